@@ -1,0 +1,616 @@
+// xcape_oracle.cpp — CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+//
+// A from-scratch C++ restatement of the algorithms of the reference's eight
+// f2py Fortran modules (xgcm/xcape v0.1.4, /root/reference/src/xcape/fortran).
+// It exists so that the CUDA product path (xcape_b200/csrc) can be checked
+// against the reference's arithmetic.  Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may load this library; the
+// product path never does.
+//
+// PARITY STATUS: pinned.  tests/test_oracle_golden.py checks this file against
+// every golden vector the reference's own tests hold for the path
+// (test/fixtures.py dataset_soundings + dataset_ERA5pressurelevel, committed
+// as tests/golden/*.npz by tests/make_golden.py).  The reference itself cannot
+// be compiled in this image (no Fortran compiler, no numpy.distutils/meson).
+//
+// Arithmetic contract (SURVEY.md §7 "Hard parts", Appendix A.8):
+//   * CAPE chain: IEEE binary32 add/mul/div, no FMA contraction
+//     (compile with -ffp-contract=off); ML accumulators binary64.
+//   * transcendentals selectable per call (`tmode`):
+//       0 = LIBM : glibc expf/logf/powf  (what gfortran's runtime links)
+//       1 = CR   : (float)exp((double)x) etc. — correctly-rounded binary32
+//       2 = SPEC : the deterministic double-precision algorithms of DESIGN.md
+//                  §"SPEC math" (explicit fma; only IEEE +,-,*,fma and integer
+//                  ops), which the CUDA kernel implements independently —
+//                  oracle(SPEC) and the GPU agree bit for bit by construction.
+//   * stdheight / SREH: binary64 with the reference's single-precision
+//     literals; Bunkers: binary32.
+//
+// Each function cites the reference file:line it follows.
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+#include <algorithm>
+
+#if defined(__GNUC__)
+#define XC_FMA_TARGET __attribute__((target("fma")))
+#else
+#define XC_FMA_TARGET
+#endif
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// SPEC math (DESIGN.md §SPEC math).  binary64 internals, binary32 in/out.
+// ---------------------------------------------------------------------------
+inline double bits2d(uint64_t b) { double d; std::memcpy(&d, &b, 8); return d; }
+inline uint64_t d2bits(double d) { uint64_t b; std::memcpy(&b, &d, 8); return b; }
+
+constexpr double SP_L2E    = 0x1.71547652b82fep+0;   // log2(e)
+constexpr double SP_LN2_HI = 0x1.62e42fee00000p-1;   // fdlibm split of ln 2
+constexpr double SP_LN2_LO = 0x1.a39ef35793c76p-33;
+constexpr double SP_MAGIC  = 6755399441055744.0;     // 1.5 * 2^52
+
+XC_FMA_TARGET inline double spec_exp_d(double x) {
+  if (!(x > -700.0)) return (x != x) ? x : 0.0;
+  if (x > 700.0) return INFINITY;
+  double nd = (x * SP_L2E + SP_MAGIC) - SP_MAGIC;   // round-to-nearest-integer (RN mode, no re-association)
+  double r = __builtin_fma(-nd, SP_LN2_HI, x);
+  r = __builtin_fma(-nd, SP_LN2_LO, r);
+  double p = 0x1.ae64567f544e4p-26;            // 1/11!
+  p = __builtin_fma(p, r, 0x1.27e4fb7789f5cp-22);  // 1/10!
+  p = __builtin_fma(p, r, 0x1.71de3a556c734p-19);  // 1/9!
+  p = __builtin_fma(p, r, 0x1.a01a01a01a01ap-16);  // 1/8!
+  p = __builtin_fma(p, r, 0x1.a01a01a01a01ap-13);  // 1/7!
+  p = __builtin_fma(p, r, 0x1.6c16c16c16c17p-10);  // 1/6!
+  p = __builtin_fma(p, r, 0x1.1111111111111p-7);   // 1/5!
+  p = __builtin_fma(p, r, 0x1.5555555555555p-5);   // 1/4!
+  p = __builtin_fma(p, r, 0x1.5555555555555p-3);   // 1/3!
+  p = __builtin_fma(p, r, 0.5);
+  p = __builtin_fma(p, r, 1.0);
+  p = __builtin_fma(p, r, 1.0);
+  int64_t n = (int64_t)nd;
+  return bits2d(d2bits(p) + ((uint64_t)n << 52));
+}
+
+// natural log of a positive, finite, NORMAL binary64 (every positive finite
+// binary32 converts to one).
+XC_FMA_TARGET inline double spec_log_d(double x) {
+  if (!(x > 0.0)) return (x == 0.0) ? -INFINITY : NAN;
+  if (x == INFINITY) return x;
+  uint64_t b = d2bits(x);
+  int64_t e = (int64_t)(b >> 52) - 1023;
+  double m = bits2d((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);  // [1,2)
+  if (m > 0x1.6a09e667f3bcdp+0) { m = m * 0.5; e += 1; }                  // (sqrt.5, sqrt2]
+  double f = m - 1.0;
+  double d = m + 1.0;
+  double y = __builtin_fma(-0.2391, d, 0.98525);   // linear seed for 1/d on [1.707, 2.414]
+  double t = __builtin_fma(-d, y, 1.0); y = __builtin_fma(y, t, y);
+  t = __builtin_fma(-d, y, 1.0); y = __builtin_fma(y, t, y);
+  t = __builtin_fma(-d, y, 1.0); y = __builtin_fma(y, t, y);
+  double s = f * y;
+  double z = s * s;
+  double q = 0x1.1111111111111p-4;                 // 1/15
+  q = __builtin_fma(q, z, 0x1.3b13b13b13b14p-4);   // 1/13
+  q = __builtin_fma(q, z, 0x1.745d1745d1746p-4);   // 1/11
+  q = __builtin_fma(q, z, 0x1.c71c71c71c71cp-4);   // 1/9
+  q = __builtin_fma(q, z, 0x1.2492492492492p-3);   // 1/7
+  q = __builtin_fma(q, z, 0x1.999999999999ap-3);   // 1/5
+  q = __builtin_fma(q, z, 0x1.5555555555555p-2);   // 1/3
+  q = __builtin_fma(q, z, 1.0);
+  double lm = (s + s) * q;
+  double ed = (double)e;
+  double r = __builtin_fma(ed, SP_LN2_LO, lm);
+  return __builtin_fma(ed, SP_LN2_HI, r);
+}
+
+enum { T_LIBM = 0, T_CR = 1, T_SPEC = 2 };
+
+template <int TM> inline float t_exp(float x) {
+  if (TM == T_LIBM) return expf(x);
+  if (TM == T_CR) return (float)exp((double)x);
+  return (float)spec_exp_d((double)x);
+}
+template <int TM> inline float t_log(float x) {
+  if (TM == T_LIBM) return logf(x);
+  if (TM == T_CR) return (float)log((double)x);
+  return (float)spec_log_d((double)x);
+}
+template <int TM> inline float t_pow(float x, float y) {
+  if (TM == T_LIBM) return powf(x, y);
+  if (TM == T_CR) return (float)pow((double)x, (double)y);
+  return (float)spec_exp_d((double)y * spec_log_d((double)x));
+}
+
+inline float fmin_(float a, float b) { return (a < b) ? a : b; }   // Fortran MIN/MAX on NaN-free data
+inline float fmax_(float a, float b) { return (a > b) ? a : b; }
+
+// ---------------------------------------------------------------------------
+// CAPE — getcape_ml == getcape_pl  (CAPE_CODE_model_lev.f90:97-564,
+// CAPE_CODE_pressure_lev.f90:174-642; helper functions :570-620)
+// ---------------------------------------------------------------------------
+// constants: CAPE_CODE_model_lev.f90:188-211, every derived one folded in binary32
+constexpr float c_g = 9.81f, c_p00 = 100000.0f, c_cp = 1005.7f, c_rd = 287.04f, c_rv = 461.5f;
+constexpr float c_xlv = 2501000.0f, c_xls = 2836017.0f, c_t0 = 273.15f;
+constexpr float c_cpv = 1875.0f, c_cpl = 4190.0f, c_cpi = 2118.636f;
+constexpr float c_lv1 = c_xlv + (c_cpl - c_cpv) * c_t0;
+constexpr float c_lv2 = c_cpl - c_cpv;
+constexpr float c_ls1 = c_xls + (c_cpi - c_cpv) * c_t0;
+constexpr float c_ls2 = c_cpi - c_cpv;
+constexpr float c_rp00 = 1.0f / c_p00;
+constexpr float c_reps = c_rv / c_rd;
+constexpr float c_rddcp = c_rd / c_cp;
+constexpr float c_cpdg = c_cp / c_g;
+constexpr float c_converge = 0.0002f;
+constexpr float c_eps_q = 287.04f / 461.5f;   // getqvs/getqvi local eps (f90:575,592)
+
+template <int TM> inline float getqvs(float p, float t) {      // f90:570-581
+  float es = 611.2f * t_exp<TM>(17.67f * (t - 273.15f) / (t - 29.65f));
+  return c_eps_q * es / (p - es);
+}
+template <int TM> inline float getqvi(float p, float t) {      // f90:587-598
+  float es = 611.2f * t_exp<TM>(21.8745584f * (t - 273.15f) / (t - 7.66f));
+  return c_eps_q * es / (p - es);
+}
+template <int TM> inline float getthe(float p, float t, float td, float q) {   // f90:604-620
+  float tlcl;
+  if ((td - t) >= -0.1f) tlcl = t;
+  else tlcl = 56.0f + 1.0f / (1.0f / (td - 56.0f) + 0.00125f * t_log<TM>(t / td));
+  return t * t_pow<TM>(100000.0f / p, 0.2854f * (1.0f - 0.28f * q)) *
+         t_exp<TM>(((3376.0f / tlcl) - 2.54f) * q * (1.0f + 0.81f * q));
+}
+
+struct ColOut { float cape, cin, zout; int32_t mulvl; int32_t n_iter, n_sub, status; };
+enum { ST_OK = 0, ST_SKIPPED = 1, ST_NONCONV = 2 };
+constexpr int NLOOP_CAP = 1 << 20;   // guard for garbage dp/pinc (documented; unreachable on valid data)
+
+// One column.  pA/tA/tdA hold nk_in levels with stride `ls` (elements).
+template <int TM>
+void getcape(const float* pA, const float* tA, const float* tdA, int64_t ls_p, int64_t ls,
+             float ps_in, float ts_in, float tds_in, float pinc, int source, float ml_depth,
+             int adiabat, int nk_in, std::vector<float>& w, ColOut& o) {
+  const int nk = nk_in + 1;                                    // f90:219
+  w.resize((size_t)7 * (nk + 2));
+  float* p = w.data();          // 1-based
+  float* t = p + (nk + 2);
+  float* td = t + (nk + 2);
+  float* pi = td + (nk + 2);
+  float* q = pi + (nk + 2);
+  float* th = q + (nk + 2);
+  float* thv = th + (nk + 2);
+  std::vector<float> zv((size_t)nk + 2);
+  float* z = zv.data();
+
+  // f90:220-240: prepend surface, convert to mks, pi, q, th, thv
+  for (int k = 1; k <= nk; ++k) {
+    float pin = (k == 1) ? ps_in : pA[(int64_t)(k - 2) * ls_p];
+    float tin = (k == 1) ? ts_in : tA[(int64_t)(k - 2) * ls];
+    float tdin = (k == 1) ? tds_in : tdA[(int64_t)(k - 2) * ls];
+    p[k] = 100.0f * pin;
+    t[k] = 273.15f + tin;
+    td[k] = 273.15f + tdin;
+    pi[k] = t_pow<TM>(p[k] * c_rp00, c_rddcp);
+    q[k] = getqvs<TM>(p[k], td[k]);
+    th[k] = t[k] / pi[k];
+    thv[k] = th[k] * (1.0f + c_reps * q[k]) / (1.0f + q[k]);
+  }
+  // f90:244-248
+  z[1] = 0.0f;
+  for (int k = 2; k <= nk; ++k) {
+    float dz = -c_cpdg * 0.5f * (thv[k] + thv[k - 1]) * (pi[k] - pi[k - 1]);
+    z[k] = z[k - 1] + dz;
+  }
+  o.mulvl = -999999;                                            // f90:252-253
+  o.zout = -999999.0f;
+  o.cape = 0.0f; o.cin = 0.0f;
+  o.n_iter = 0; o.n_sub = 0; o.status = ST_OK;
+
+  int kmax = 1;
+  double avgth = 0.0, avgqv = 0.0;
+  float th2 = 0, qv2 = 0;
+  if (source == 1) {                                            // f90:257-259
+    kmax = 1;
+  } else if (source == 2) {                                     // f90:261-281
+    if (p[1] < 50000.0f) {
+      kmax = 1;
+    } else {
+      float maxthe = 0.0f;
+      for (int k = 1; k <= nk; ++k) {
+        if (p[k] >= 50000.0f) {
+          float the = getthe<TM>(p[k], t[k], td[k], q[k]);
+          if (the > maxthe) { o.mulvl = k; maxthe = the; kmax = k; }
+        }
+      }
+    }
+  } else {                                                      // f90:284-339 (source 3)
+    if ((z[2] - z[1]) > ml_depth) {
+      avgth = th[1]; avgqv = q[1]; kmax = 1;
+    } else if (z[nk] < ml_depth) {
+      avgth = th[nk]; avgqv = q[nk]; kmax = nk;
+    } else {
+      avgth = 0.0; avgqv = 0.0;
+      int k = 2;
+      // reference: do while((z(k).le.ml_depth).and.(k.le.nk)) — reads z(nk+1) when
+      // z(nk)==ml_depth exactly; guarded here (k bound first).
+      while (k <= nk && z[k] <= ml_depth) {
+        avgth = avgth + (double)(0.5f * (z[k] - z[k - 1]) * (th[k] + th[k - 1]));
+        avgqv = avgqv + (double)(0.5f * (z[k] - z[k - 1]) * (q[k] + q[k - 1]));
+        k = k + 1;
+      }
+      if (k > nk) k = nk;   // only on the guarded edge above
+      th2 = th[k - 1] + (th[k] - th[k - 1]) * (ml_depth - z[k - 1]) / (z[k] - z[k - 1]);
+      qv2 = q[k - 1] + (q[k] - q[k - 1]) * (ml_depth - z[k - 1]) / (z[k] - z[k - 1]);
+      avgth = avgth + (double)(0.5f * (ml_depth - z[k - 1]) * (th2 + th[k - 1]));
+      avgqv = avgqv + (double)(0.5f * (ml_depth - z[k - 1]) * (qv2 + q[k - 1]));
+      avgth = avgth / (double)ml_depth;
+      avgqv = avgqv / (double)ml_depth;
+      kmax = 1;
+    }
+  }
+
+  // f90:355-383 parcel initial state
+  float narea = 0.0f;
+  int k = kmax;
+  float pi2, p2, t2, thv2, b2;
+  if (source == 1 || source == 2) {
+    th2 = th[kmax]; pi2 = pi[kmax]; p2 = p[kmax]; t2 = t[kmax];
+    thv2 = thv[kmax]; qv2 = q[kmax]; b2 = 0.0f;
+  } else {
+    th2 = (float)avgth; qv2 = (float)avgqv;
+    thv2 = th2 * (1.0f + c_reps * qv2) / (1.0f + qv2);
+    pi2 = pi[kmax]; p2 = p[kmax]; t2 = th2 * pi2;
+    b2 = c_g * (thv2 - thv[kmax]) / thv[kmax];
+  }
+  float ql2 = 0.0f, qi2 = 0.0f, qt = qv2;
+  float cape = 0.0f, cin = 0.0f;
+  bool doit = true;
+  const bool ice = !(adiabat == 1 || adiabat == 2);
+  const bool pseudo = (adiabat == 1 || adiabat == 3);
+
+  // f90:403-559 ascent
+  while (doit && k < nk) {
+    k = k + 1;
+    float b1 = b2;
+    float dp = p[k - 1] - p[k];
+    int nloop;
+    if (dp < pinc) {
+      nloop = 1;
+    } else {
+      float r = dp / pinc;
+      nloop = (r < (float)NLOOP_CAP) ? 1 + (int)r : NLOOP_CAP;
+      dp = dp / (float)nloop;
+    }
+    for (int n = 1; n <= nloop; ++n) {
+      float p1 = p2, t1 = t2, th1 = th2, qv1 = qv2, ql1 = ql2, qi1 = qi2;
+      p2 = p2 - dp;
+      pi2 = t_pow<TM>(p2 * c_rp00, c_rddcp);
+      float thlast = th1;
+      int i = 0;
+      bool not_converged = true;
+      o.n_sub++;
+      while (not_converged) {
+        i = i + 1;
+        t2 = thlast * pi2;
+        float fliq, fice;
+        if (ice) {
+          fliq = fmax_(fmin_((t2 - 233.15f) / (273.15f - 233.15f), 1.0f), 0.0f);
+          fice = 1.0f - fliq;
+        } else { fliq = 1.0f; fice = 0.0f; }
+        qv2 = fmin_(qt, fliq * getqvs<TM>(p2, t2) + fice * getqvi<TM>(p2, t2));
+        qi2 = fmax_(fice * (qt - qv2), 0.0f);
+        ql2 = fmax_(qt - qv2 - qi2, 0.0f);
+        float tbar = 0.5f * (t1 + t2);
+        float qvbar = 0.5f * (qv1 + qv2);
+        float qlbar = 0.5f * (ql1 + ql2);
+        float qibar = 0.5f * (qi1 + qi2);
+        float lhv = c_lv1 - c_lv2 * tbar;
+        float lhs = c_ls1 - c_ls2 * tbar;
+        float rm = c_rd + c_rv * qvbar;
+        float cpm = c_cp + c_cpv * qvbar + c_cpl * qlbar + c_cpi * qibar;
+        th2 = th1 * t_exp<TM>(lhv * (ql2 - ql1) / (cpm * tbar) + lhs * (qi2 - qi1) / (cpm * tbar) +
+                              (rm / cpm - c_rddcp) * t_log<TM>(p2 / p1));
+        o.n_iter++;
+        if (i > 100) {                                           // f90:464-474
+          o.cape = 0.0f; o.cin = 0.0f; o.status = ST_NONCONV;
+          return;                                                // mulvl/zout keep current values
+        }
+        if (std::fabs(th2 - thlast) > c_converge) thlast = thlast + 0.3f * (th2 - thlast);
+        else not_converged = false;
+      }
+      if (pseudo) { qt = qv2; ql2 = 0.0f; qi2 = 0.0f; }          // f90:487-491
+    }
+    thv2 = th2 * (1.0f + c_reps * qv2) / (1.0f + qv2 + ql2 + qi2);   // f90:501-503
+    b2 = c_g * (thv2 - thv[k]) / thv[k];
+    float dz = -c_cpdg * 0.5f * (thv[k] + thv[k - 1]) * (pi[k] - pi[k - 1]);
+    float parea;
+    if (b2 >= 0.0f && b1 < 0.0f) {                               // f90:509-545
+      float frac = b2 / (b2 - b1);
+      parea = 0.5f * b2 * dz * frac;
+      narea = narea - 0.5f * b1 * dz * (1.0f - frac);
+      cin = cin + narea;
+      narea = 0.0f;
+    } else if (b2 < 0.0f && b1 > 0.0f) {
+      float frac = b1 / (b1 - b2);
+      parea = 0.5f * b1 * dz * frac;
+      narea = -0.5f * b2 * dz * (1.0f - frac);
+    } else if (b2 < 0.0f) {
+      parea = 0.0f;
+      narea = narea - 0.5f * dz * (b1 + b2);
+    } else {
+      parea = 0.5f * dz * (b1 + b2);
+      narea = 0.0f;
+    }
+    cape = cape + fmax_(0.0f, parea);
+    if (p[k] <= 10000.0f && b2 < 0.0f) doit = false;             // f90:554-557
+    o.zout = z[k];                                               // f90:558
+  }
+  o.cape = cape; o.cin = cin;
+}
+
+template <int TM>
+void loopcape_range(int64_t i0, int64_t i1, const float* p3d, const float* t3d, const float* td3d,
+                    bool p_is_1d, const float* ps, const float* ts, const float* tds, float pinc,
+                    int source, float ml_depth, int adiabat, const int32_t* start_3d, int nk,
+                    float* cape, float* cin, int32_t* mulvl, float* zout, int32_t* n_iter,
+                    int32_t* n_sub, int32_t* status) {
+  std::vector<float> w;
+  for (int64_t i = i0; i < i1; ++i) {
+    ColOut o;
+    if (ts[i] > 0.0f) {                                          // f90:77 / pressure_lev.f90:152
+      int ks = start_3d ? start_3d[i] : 1;                       // pressure_lev.f90:154-160
+      if (ks < 1) ks = 1;
+      if (ks > nk) ks = nk;
+      int nk_used = nk - ks + 1;
+      const float* pcol = p_is_1d ? p3d + (ks - 1) : p3d + i * nk + (ks - 1);
+      getcape<TM>(pcol, t3d + i * nk + (ks - 1), td3d + i * nk + (ks - 1), 1, 1, ps[i], ts[i],
+                  tds[i], pinc, source, ml_depth, adiabat, nk_used, w, o);
+    } else {
+      o.cape = 0; o.cin = 0; o.zout = 0; o.mulvl = 0; o.n_iter = 0; o.n_sub = 0; o.status = ST_SKIPPED;
+    }
+    cape[i] = o.cape; cin[i] = o.cin; mulvl[i] = o.mulvl; zout[i] = o.zout;
+    if (n_iter) n_iter[i] = o.n_iter;
+    if (n_sub) n_sub[i] = o.n_sub;
+    if (status) status[i] = o.status;
+  }
+}
+
+template <class F> void par_for(int64_t n, int nthreads, F f) {
+  if (nthreads <= 1 || n < 2) { f(0, n); return; }
+  std::vector<std::thread> th;
+  int64_t blk = (n + nthreads - 1) / nthreads;
+  for (int t = 0; t < nthreads; ++t) {
+    int64_t a = std::min<int64_t>(n, t * blk), b = std::min<int64_t>(n, a + blk);
+    if (a < b) th.emplace_back([=] { f(a, b); });
+  }
+  for (auto& x : th) x.join();
+}
+
+// ---------------------------------------------------------------------------
+// stdheight  (stdheight_2D_model_lev.f90:74-160; pressure: stdheight_2D_pressure_lev.f90:65-93,133-219)
+// binary64 arithmetic, single-precision literals promoted
+// ---------------------------------------------------------------------------
+constexpr double h_R = (double)287.04f, h_g = (double)-9.80665f, h_eps = (double)0.6219800858985514f;
+constexpr double h_t0 = (double)273.15f, h_c1 = (double)6.112f, h_c2 = (double)53.49f, h_c3 = (double)5.09f;
+
+inline double tvirt(double T, double Td, double P) {
+  double Tin = T + h_t0;
+  double Tdin = Td + h_t0;
+  double E = h_c1 * std::exp((h_c2 - (6808 / Tdin) - h_c3 * std::log(Tdin)));
+  double w = h_eps * (E / (P - E));
+  return Tin * ((w + h_eps) / (h_eps * (1 + w)));
+}
+// P,T,Td: nk levels, unit stride; H out nk
+void stdheight_col(const double* P, const double* T, const double* Td, double Ps, double Ts,
+                   double Tds, double Hin, int nk, double* H, double* Hs) {
+  double Tvs = tvirt(Ts, Tds, Ps);
+  *Hs = Hin;
+  double Tvprev = Tvs, Hprev = Hin, Pprev = Ps;
+  for (int k = 0; k < nk; ++k) {
+    double Tv = tvirt(T[k], Td[k], P[k]);
+    double h = Hprev + ((h_R * ((Tv + Tvprev) / 2) / h_g)) * (std::log(P[k] / Pprev));
+    H[k] = h; Hprev = h; Tvprev = Tv; Pprev = P[k];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Bunkers (Bunkers_model_lev.f90:75-180, DINTERP2DZ :188-236) — binary32
+// ---------------------------------------------------------------------------
+float dinterp2dz(const float* V, const float* Z, float height, int nz) {   // 0-based arrays of nz
+  float out = -999999.0f;
+  int ip = 0, im = 1;
+  if (Z[0] > Z[nz - 1]) { ip = 1; im = 0; }
+  for (int kp = nz; kp >= 2; --kp) {                     // KP is 1-based in the reference
+    float zlo = Z[kp - im - 1], zhi = Z[kp - ip - 1];
+    if (zlo <= height && zhi > height) {
+      float w2 = (height - zlo) / (zhi - zlo);
+      float w1 = (float)(1.0 - (double)w2);              // 1.D0 - W2 (f90:228)
+      out = w1 * V[kp - im - 1] + w2 * V[kp - ip - 1];
+      break;
+    }
+  }
+  return out;
+}
+void bunkers_col(const float* U, const float* V, const float* Z, int nk, float* RM, float* LM, float* M6) {
+  float us[13], vs[13];
+  us[0] = U[0]; vs[0] = V[0];
+  for (int i = 1; i < 13; ++i) {
+    float lvl = 500.0f * (float)i;
+    us[i] = dinterp2dz(U, Z, lvl, nk);
+    vs[i] = dinterp2dz(V, Z, lvl, nk);
+  }
+  float mu = 0.0f, mv = 0.0f;                            // f2py zero-fills intent(out) (SURVEY B-8)
+  for (int i = 0; i < 13; ++i) { mu = mu + us[i]; mv = mv + vs[i]; }
+  mu = mu / 13.0f; mv = mv / 13.0f;
+  float uu = 0.0f, vu = 0.0f, ud = 0.0f, vd = 0.0f;      // uninitialised in the reference; 0 reproduces goldens
+  for (int i = 11; i < 13; ++i) { uu = uu + us[i]; vu = vu + vs[i]; }
+  uu = uu / 2.0f; vu = vu / 2.0f;
+  for (int i = 0; i < 2; ++i) { ud = ud + us[i]; vd = vd + vs[i]; }
+  ud = ud / 2.0f; vd = vd / 2.0f;
+  float ushr = uu - ud, vshr = vu - vd;
+  float nrm = sqrtf(ushr * ushr + vshr * vshr);          // (..)**0.5
+  RM[0] = mu + 7.5f * vshr / nrm;
+  RM[1] = mv - 7.5f * ushr / nrm;
+  LM[0] = mu - 7.5f * vshr / nrm;
+  LM[1] = mv + 7.5f * ushr / nrm;
+  M6[0] = mu; M6[1] = mv;
+}
+
+// ---------------------------------------------------------------------------
+// SREH (SREH_model_lev.f90:61-129) — binary64
+// ---------------------------------------------------------------------------
+inline double interp1(double y1, double y3, double x1, double x2, double x3) {
+  if (x3 == x1) x1 = x1 - (double)0.01f;
+  return y1 + ((y3 - y1) * ((x2 - x1) / (x3 - x1)));
+}
+void sreh_col(const double* u, const double* v, const double* z, double curm, double cvrm,
+              double culm, double cvlm, double top, int nk, double* srm, double* slm,
+              std::vector<double>& w) {
+  w.resize((size_t)2 * nk);
+  double* ut = w.data(); double* vt = ut + nk;
+  for (int k = 0; k < nk; ++k) { ut[k] = u[k]; vt[k] = v[k]; }
+  int ktop = 0;                                           // 1-based
+  for (int k = 2; k <= nk; ++k) {
+    if (z[k - 1] > top && ktop == 0) {
+      ktop = k;
+      ut[k - 1] = interp1(u[k - 1], u[k - 2], z[k - 1], top, z[k - 2]);
+      vt[k - 1] = interp1(v[k - 1], v[k - 2], z[k - 1], top, z[k - 2]);
+    }
+  }
+  double s = 0.0;
+  for (int k = 2; k <= ktop; ++k)
+    s = s + (((ut[k - 1] - curm) * (vt[k - 1] - vt[k - 2])) - ((vt[k - 1] - cvrm) * (ut[k - 1] - ut[k - 2])));
+  *srm = -s;
+  s = 0.0;
+  for (int k = 2; k <= ktop; ++k)
+    s = s + (((ut[k - 1] - culm) * (vt[k - 1] - vt[k - 2])) - ((vt[k - 1] - cvlm) * (ut[k - 1] - ut[k - 2])));
+  *slm = -s;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C entry points.  Array layout = the f2py layout: (nk, n2) Fortran order, i.e.
+// element (k, i) at [i*nk + k]  (each column contiguous).
+// ===========================================================================
+extern "C" {
+
+// CAPE_CODE_model_lev.pyf:6-24 / f90:4-91
+int xcape_ref_loopcape_ml(const float* p3d, const float* t3d, const float* td3d, const float* ps,
+                          const float* ts, const float* tds, float pinc, int source, float ml_depth,
+                          int adiabat, int nk, int64_t n2, float* cape, float* cin, int32_t* mulvl,
+                          float* zout, int tmode, int nthreads, int32_t* n_iter, int32_t* n_sub,
+                          int32_t* status) {
+  if (source < 1 || source > 3 || adiabat < 1 || adiabat > 4 || !(pinc > 0.0f) || nk < 1) return 1;
+  par_for(n2, nthreads, [=](int64_t a, int64_t b) {
+    if (tmode == T_LIBM) loopcape_range<T_LIBM>(a, b, p3d, t3d, td3d, false, ps, ts, tds, pinc, source, ml_depth, adiabat, nullptr, nk, cape, cin, mulvl, zout, n_iter, n_sub, status);
+    else if (tmode == T_CR) loopcape_range<T_CR>(a, b, p3d, t3d, td3d, false, ps, ts, tds, pinc, source, ml_depth, adiabat, nullptr, nk, cape, cin, mulvl, zout, n_iter, n_sub, status);
+    else loopcape_range<T_SPEC>(a, b, p3d, t3d, td3d, false, ps, ts, tds, pinc, source, ml_depth, adiabat, nullptr, nk, cape, cin, mulvl, zout, n_iter, n_sub, status);
+  });
+  return 0;
+}
+
+// CAPE_CODE_pressure_lev.pyf:26-45 / f90:88-169   (p is (nk,1); start_3d 1-based)
+int xcape_ref_loopcape_pl1d(const float* t3d, const float* td3d, const float* p1d, const float* ps,
+                            const float* ts, const float* tds, float pinc, int source,
+                            float ml_depth, int adiabat, const int32_t* start_3d, int nk,
+                            int64_t n2, float* cape, float* cin, int32_t* mulvl, float* zout,
+                            int tmode, int nthreads, int32_t* n_iter, int32_t* n_sub,
+                            int32_t* status) {
+  if (source < 1 || source > 3 || adiabat < 1 || adiabat > 4 || !(pinc > 0.0f) || nk < 1) return 1;
+  par_for(n2, nthreads, [=](int64_t a, int64_t b) {
+    if (tmode == T_LIBM) loopcape_range<T_LIBM>(a, b, p1d, t3d, td3d, true, ps, ts, tds, pinc, source, ml_depth, adiabat, start_3d, nk, cape, cin, mulvl, zout, n_iter, n_sub, status);
+    else if (tmode == T_CR) loopcape_range<T_CR>(a, b, p1d, t3d, td3d, true, ps, ts, tds, pinc, source, ml_depth, adiabat, start_3d, nk, cape, cin, mulvl, zout, n_iter, n_sub, status);
+    else loopcape_range<T_SPEC>(a, b, p1d, t3d, td3d, true, ps, ts, tds, pinc, source, ml_depth, adiabat, start_3d, nk, cape, cin, mulvl, zout, n_iter, n_sub, status);
+  });
+  return 0;
+}
+
+// stdheight_2D_model_lev.pyf:6-19 / f90:4-34
+int xcape_ref_loop_stdheight_ml(const double* P, const double* T, const double* Td, const double* Ps,
+                                const double* Ts, const double* Tds, const double* Hin, int nk,
+                                int64_t nx, double* H, double* Hs, int nthreads) {
+  par_for(nx, nthreads, [=](int64_t a, int64_t b) {
+    for (int64_t i = a; i < b; ++i)
+      stdheight_col(P + i * nk, T + i * nk, Td + i * nk, Ps[i], Ts[i], Tds[i], Hin[i], nk, H + i * nk, Hs + i);
+  });
+  return 0;
+}
+
+// stdheight_2D_pressure_lev.pyf:21-35 / f90:65-93  (start_3d arrives as double)
+int xcape_ref_loop_stdheight_pl1d(const double* T, const double* Td, const double* P1d,
+                                  const double* Ps, const double* Ts, const double* Tds,
+                                  const double* Hin, const double* start_3d, int nk, int64_t nx,
+                                  double* H, double* Hs, int nthreads) {
+  par_for(nx, nthreads, [=](int64_t a, int64_t b) {
+    for (int64_t i = a; i < b; ++i) {
+      int ks = (int)start_3d[i];
+      if (ks < 1) ks = 1;
+      if (ks > nk) ks = nk;
+      for (int k = 0; k < ks - 1; ++k) H[i * nk + k] = -999999;
+      stdheight_col(P1d + (ks - 1), T + i * nk + (ks - 1), Td + i * nk + (ks - 1), Ps[i], Ts[i],
+                    Tds[i], Hin[i], nk - ks + 1, H + i * nk + (ks - 1), Hs + i);
+    }
+  });
+  return 0;
+}
+
+// Bunkers_model_lev.pyf:8-21 (start_3d == NULL) / Bunkers_pressure_lev.pyf:6-20 (start_3d real)
+// RM/LM/Mean6 are (2, n2) Fortran order: element (c, i) at [i*2 + c].
+int xcape_ref_bunkers_loop(const float* U, const float* V, const float* Z, const float* Us,
+                           const float* Vs, const float* Zs, const float* start_3d, int nk,
+                           int64_t n2, float* RM, float* LM, float* M6, int nthreads) {
+  par_for(n2, nthreads, [=](int64_t a, int64_t b) {
+    std::vector<float> ua(nk + 1), va(nk + 1), za(nk + 1);
+    for (int64_t i = a; i < b; ++i) {
+      int ks = start_3d ? (int)start_3d[i] : 1;
+      if (ks < 1) ks = 1;
+      if (ks > nk) ks = nk;
+      int n = nk - ks + 1;
+      ua[0] = Us[i]; va[0] = Vs[i]; za[0] = Zs[i];
+      for (int k = 0; k < n; ++k) { ua[k + 1] = U[i * nk + ks - 1 + k]; va[k + 1] = V[i * nk + ks - 1 + k]; za[k + 1] = Z[i * nk + ks - 1 + k]; }
+      bunkers_col(ua.data(), va.data(), za.data(), n + 1, RM + 2 * i, LM + 2 * i, M6 + 2 * i);
+    }
+  });
+  return 0;
+}
+
+// SREH_model_lev.pyf:6-23 (start_3d == NULL) / SREH_pressure_lev.pyf:6-24 (start_3d double)
+int xcape_ref_loop_sreh(const double* u, const double* v, const double* z, const double* us,
+                        const double* vs, const double* zs, const double* cu_rm, const double* cv_rm,
+                        const double* cu_lm, const double* cv_lm, double top, const double* start_3d,
+                        int nk, int64_t n2, double* srm, double* slm, int nthreads) {
+  par_for(n2, nthreads, [=](int64_t a, int64_t b) {
+    std::vector<double> ua(nk + 1), va(nk + 1), za(nk + 1), w;
+    for (int64_t i = a; i < b; ++i) {
+      int ks = start_3d ? (int)start_3d[i] : 1;
+      if (ks < 1) ks = 1;
+      if (ks > nk) ks = nk;
+      int n = nk - ks + 1;
+      ua[0] = us[i]; va[0] = vs[i]; za[0] = zs[i];
+      for (int k = 0; k < n; ++k) { ua[k + 1] = u[i * nk + ks - 1 + k]; va[k + 1] = v[i * nk + ks - 1 + k]; za[k + 1] = z[i * nk + ks - 1 + k]; }
+      sreh_col(ua.data(), va.data(), za.data(), cu_rm[i], cv_rm[i], cu_lm[i], cv_lm[i], top, n + 1, srm + i, slm + i, w);
+    }
+  });
+  return 0;
+}
+
+// scalar probes of the transcendental modes (tests compare SPEC vs CR vs LIBM)
+float xcape_ref_expf(float x, int tmode) { return tmode == 0 ? t_exp<0>(x) : tmode == 1 ? t_exp<1>(x) : t_exp<2>(x); }
+float xcape_ref_logf(float x, int tmode) { return tmode == 0 ? t_log<0>(x) : tmode == 1 ? t_log<1>(x) : t_log<2>(x); }
+float xcape_ref_powf(float x, float y, int tmode) { return tmode == 0 ? t_pow<0>(x, y) : tmode == 1 ? t_pow<1>(x, y) : t_pow<2>(x, y); }
+void xcape_ref_expf_v(const float* x, float* y, int64_t n, int tmode) { for (int64_t i = 0; i < n; ++i) y[i] = xcape_ref_expf(x[i], tmode); }
+void xcape_ref_logf_v(const float* x, float* y, int64_t n, int tmode) { for (int64_t i = 0; i < n; ++i) y[i] = xcape_ref_logf(x[i], tmode); }
+void xcape_ref_powf_v(const float* x, const float* e, float* y, int64_t n, int tmode) { for (int64_t i = 0; i < n; ++i) y[i] = xcape_ref_powf(x[i], e[i], tmode); }
+
+int xcape_ref_fp_contract(void) {
+#ifdef XC_ORACLE_CONTRACT
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+}  // extern "C"
