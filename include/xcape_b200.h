@@ -1,0 +1,124 @@
+/* xcape_b200.h — C ABI of libxcape_b200.so (B200 / sm_100a column kernels for xcape).
+ *
+ * This is the drop-in boundary for the reference's per-column hot path.  The reference
+ * (xgcm/xcape v0.1.4) crosses from Python to native code through eight f2py routines
+ * (src/xcape/fortran/\*.pyf); every entry point below names the routine(s) it replaces.
+ * Plain pointers and sizes only: no torch / cupy / numpy types.  Every function returns an
+ * int status (0 = XCAPE_OK), never throws and never aborts the process (the reference's
+ * Fortran `stop` on a bad enum, CAPE_CODE_model_lev.f90:343-352,492-497, becomes
+ * XCAPE_ERR_ARG).  All functions are thread-safe (the reference routines are marked
+ * `threadsafe`, e.g. CAPE_CODE_model_lev.pyf:7).
+ *
+ * Units follow the reference: pressure hPa, temperature / dew point degC, wind m/s,
+ * heights m AGL, pinc Pa, ml_depth / depth m.
+ *
+ * Array layouts for the 3-D fields (t, td, u, v, and p when p_is_1d == 0):
+ *   XCAPE_LEVEL_LAST   element (level k, column i) at [i*nlev + k]  — each column contiguous.
+ *                      This is the reference's (nk, n2) Fortran-order f2py layout and what
+ *                      core._reshape_inputs (core.py:44-50) produces from [..., nlev] arrays.
+ *   XCAPE_LEVEL_MAJOR  element (k, i) at [k*ncol + i] — structure-of-arrays by level, the
+ *                      native (time, level, lat, lon) order of ERA5/HRRR files; zero-copy
+ *                      into the kernels when dtype is XCAPE_F32.
+ * Level index 0 is the level nearest the surface (reference assumption).
+ */
+#ifndef XCAPE_B200_H
+#define XCAPE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XCAPE_OK 0
+#define XCAPE_ERR_ARG 1     /* invalid enum / size / null pointer */
+#define XCAPE_ERR_CUDA 2    /* a CUDA call failed; see xcape_cuda_last_error() */
+#define XCAPE_ERR_NODEV 3   /* no usable CUDA device */
+
+enum { XCAPE_F32 = 0, XCAPE_F64 = 1 };                 /* dtype of ALL input arrays of a call */
+enum { XCAPE_LEVEL_LAST = 0, XCAPE_LEVEL_MAJOR = 1 };  /* layout of the 3-D input arrays */
+enum { XCAPE_MEM_HOST = 0, XCAPE_MEM_DEVICE = 1 };     /* where input AND output pointers live */
+enum { XCAPE_SOURCE_SURFACE = 1, XCAPE_SOURCE_MOST_UNSTABLE = 2, XCAPE_SOURCE_MIXED_LAYER = 3 }; /* core.py:302 */
+enum { XCAPE_ADIABAT_PSEUDO_LIQUID = 1, XCAPE_ADIABAT_REVERSIBLE_LIQUID = 2,
+       XCAPE_ADIABAT_PSEUDO_ICE = 3, XCAPE_ADIABAT_REVERSIBLE_ICE = 4 };                          /* core.py:303-304 */
+/* XCAPE_FAITHFUL: IEEE binary32 chain without FMA contraction + the deterministic "SPEC"
+ * transcendentals of DESIGN.md (bit-identical to oracle tmode=SPEC).  Default. */
+enum { XCAPE_FAITHFUL = 0 };
+/* per-column status word (optional output) */
+enum { XCAPE_ST_OK = 0, XCAPE_ST_SKIPPED = 1 /* ts <= 0 degC gate, f90:77 */,
+       XCAPE_ST_NONCONVERGED = 2 /* > 100 moist iterations, f90:464-474: cape = cin = 0 */ };
+
+/* ---------------------------------------------------------------------------------------
+ * CAPE / CIN.  Replaces loopcape_ml (CAPE_CODE_model_lev.pyf:6-24, f90:4-91) when
+ * p_is_1d == 0 and loopcape_pl1d (CAPE_CODE_pressure_lev.pyf:26-45, f90:88-169) when
+ * p_is_1d == 1, including getcape_ml/getcape_pl, getqvs, getqvi, getthe (f90:97-620), and
+ * the numpy `pres_lev_pos` pre-step of core.py:286-289 when start_3d == NULL.
+ *
+ *   p        p_is_1d ? [nlev] : 3-D field           ps, ts, tds   [ncol]
+ *   t, td    3-D fields                             start_3d      [ncol] 1-based first used
+ *                                                   level (int32) or NULL (computed on device
+ *                                                   for p_is_1d, 1 otherwise)
+ *   outputs  cape, cin, zmulev float32 [ncol]; mulev int32 [ncol]; status int32 [ncol] or NULL;
+ *            n_iter int32 [ncol] or NULL = number of moist-adiabat iterations the column ran
+ *            (the work counter behind the roofline figure).
+ *            mulev / zmulev follow the reference's conventions.
+ *   mem      XCAPE_MEM_DEVICE: every pointer is a device pointer on `device`; the work is
+ *            enqueued on `stream` (a cudaStream_t / CUstream, NULL = default stream) and the
+ *            call returns without synchronising.  XCAPE_MEM_HOST: pointers are host memory;
+ *            the call stages column blocks through pinned buffers, overlaps copies with
+ *            compute, and returns when the outputs are complete (`stream` is ignored).
+ * ------------------------------------------------------------------------------------- */
+int xcape_cuda_cape(const void* p, const void* t, const void* td,
+                    const void* ps, const void* ts, const void* tds,
+                    int64_t ncol, int nlev, int p_is_1d, int dtype, int layout, int mem,
+                    int source, int adiabat, float ml_depth, float pinc,
+                    const int32_t* start_3d,
+                    float* cape, float* cin, int32_t* mulev, float* zmulev, int32_t* status,
+                    int32_t* n_iter, int precision, int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Storm-relative helicity, fused.  Replaces, in one pass over the column,
+ *   loop_stdheight_ml / loop_stdheight_pl1d  (stdheight_2D_model_lev.pyf:6-19,
+ *                                             stdheight_2D_pressure_lev.pyf:21-35),
+ *   bunkers_loop_ml / bunkers_loop_pl        (Bunkers_model_lev.pyf:8-21, Bunkers_pressure_lev.pyf:6-20),
+ *   loop_sreh_ml / loop_sreh_pl              (SREH_model_lev.pyf:6-23, SREH_pressure_lev.pyf:6-24)
+ * as chained by core._calc_srh_numpy (core.py:516-535) and srh.srh (srh.py:41-61).
+ *   srh_rm, srh_lm  float64 [ncol]
+ *   rm, lm, mean6   float32 [2*ncol] in the reference's (2, n2) Fortran order (component c of
+ *                   column i at [2*i + c]) or NULL (output_var == 'srh')
+ *   aglh0           height of the surface level (core.py passes 2.0)
+ * ------------------------------------------------------------------------------------- */
+int xcape_cuda_srh(const void* p, const void* t, const void* td, const void* u, const void* v,
+                   const void* ps, const void* ts, const void* tds, const void* us, const void* vs,
+                   int64_t ncol, int nlev, int p_is_1d, int dtype, int layout, int mem,
+                   double depth, double aglh0, const int32_t* start_3d,
+                   double* srh_rm, double* srh_lm, float* rm, float* lm, float* mean6,
+                   int precision, int device, void* stream);
+
+/* Heights only (loop_stdheight_ml / loop_stdheight_pl1d).  h is float64, same layout as the
+ * inputs' `layout`; levels below start_3d are -999999 (stdheight_2D_pressure_lev.f90:85-87);
+ * hs [ncol] = aglh0. */
+int xcape_cuda_stdheight(const void* p, const void* t, const void* td,
+                         const void* ps, const void* ts, const void* tds,
+                         int64_t ncol, int nlev, int p_is_1d, int dtype, int layout, int mem,
+                         double aglh0, const int32_t* start_3d,
+                         double* h, double* hs, int device, void* stream);
+
+/* core.py:286-289 on the device: start[i] = 1 + argmin_k { ps[i] - p[k] : ps[i] - p[k] >= 0 }
+ * (first minimum; 1 when every level is masked), evaluated in the inputs' own dtype. */
+int xcape_cuda_pres_lev_pos(const void* p, const void* ps, int64_t ncol, int nlev, int dtype,
+                            int mem, int32_t* start_3d, int device, void* stream);
+
+/* Diagnostics. */
+const char* xcape_cuda_last_error(void);      /* thread-local message of the last failure */
+int xcape_cuda_device_count(void);            /* < 0 on error */
+const char* xcape_cuda_version(void);         /* "xcape_b200 <semver> sm_100a" */
+int64_t xcape_cuda_kernel_launches(void);     /* kernels launched by this library so far (process-wide) */
+/* Measured arithmetic peaks of `device` (roofline denominators the driver's MEASURED_PEAKS.json
+ * lacks): dependent-chain-free FFMA / DFMA loops, 2 flop per FMA, best of `reps` launches. */
+int xcape_cuda_measure_peaks(int device, int reps, double* fp32_tflops, double* fp64_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XCAPE_B200_H */

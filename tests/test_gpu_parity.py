@@ -1,0 +1,338 @@
+"""Parity of the CUDA path (through the C ABI, via xcape_b200.core) against the oracle and
+against the reference's golden vectors.  Needs a B200: run with ``-m gpu``.
+
+Bars (BASELINE.json north_star / SURVEY §8d):
+  * MU level index: bit-exact (tie rule: lowest index wins, strict '>' scan);
+  * CAPE, CIN, zMUlev: bit-exact against oracle tmode=SPEC (same arithmetic by construction),
+    |d| <= max(1, 1e-4 |ref|) against oracle tmode=LIBM (what gfortran would link);
+  * reference-test tolerance on the goldens: assert_almost_equal decimal=0 (CAPE/CIN/MU),
+    decimal=5 (SRH) — test/test_core.py:62-65, 219-220.
+"""
+import numpy as np
+import pytest
+
+from conftest import close_decimal, era_cape_args, era_srh_args, snd_cape_args, snd_srh_args
+
+pytestmark = pytest.mark.gpu
+
+SOURCES = ['surface', 'most-unstable', 'mixed-layer']
+ADIABATS = ['pseudo-liquid', 'reversible-liquid', 'pseudo-ice', 'reversible-ice']
+
+
+@pytest.fixture(scope='module')
+def core():
+    from xcape_b200 import _lib, core
+    assert _lib.device_count() >= 1, 'no CUDA device visible'
+    return core
+
+
+def tol_ok(a, ref):
+    a = np.asarray(a, np.float64); ref = np.asarray(ref, np.float64)
+    return np.abs(a - ref) <= np.maximum(1.0, 1e-4 * np.abs(ref))
+
+
+def assert_bitexact(got, ref, what):
+    for g, r, name in zip(got, ref, ('cape', 'cin', 'mulev', 'zmulev')):
+        g = np.asarray(g); r = np.asarray(r)
+        bad = np.flatnonzero(g.ravel() != r.ravel())
+        assert bad.size == 0, f'{what}: {name} differs in {bad.size} columns, first {bad[:5]}: {g.ravel()[bad[:5]]} vs {r.ravel()[bad[:5]]}'
+
+
+# ------------------------------------------------------------------ goldens
+@pytest.mark.parametrize('source,pinc,gc,gi', [
+    ('surface', 100, 'SB_CAPE_pinc100', 'SB_CIN_pinc100'),
+    ('mixed-layer', 1000, 'ML_CAPE_pinc1000_mldepth500', 'ML_CIN_pinc1000_mldepth500'),
+    ('most-unstable', 100, 'MU_CAPE_pinc100', 'MU_CIN_pinc100')])
+def test_cape_sigma_goldens(core, soundings, source, pinc, gc, gi):
+    r = core.calc_cape(*snd_cape_args(soundings), source=source, ml_depth=500., adiabat='pseudo-liquid', pinc=pinc,
+                       method='cuda', vertical_lev='sigma')
+    assert len(r) == (4 if source == 'most-unstable' else 2)
+    close_decimal(r[0], soundings[gc], 0)
+    close_decimal(r[1], soundings[gi], 0)
+    assert np.array_equal(r[0], soundings[gc].astype(np.float32))
+    assert np.array_equal(r[1], soundings[gi].astype(np.float32))
+    if source == 'most-unstable':
+        assert r[2].dtype == np.int32
+        assert np.array_equal(r[2], soundings['MU_lv_pinc100'].astype(np.int32))
+        close_decimal(r[3], soundings['MU_z_pinc100'], 0)
+
+
+@pytest.mark.parametrize('source,gc,gi', [('surface', 'capesp500', 'cinsp500'),
+                                          ('mixed-layer', 'capeml300p500', 'cinml300p500'),
+                                          ('most-unstable', 'capemup500', 'cinmup500')])
+def test_cape_pressure_goldens(core, era5pl, source, gc, gi):
+    r = core.calc_cape(*era_cape_args(era5pl), source=source, ml_depth=300, adiabat='pseudo-liquid', pinc=500,
+                       method='cuda', vertical_lev='pressure')
+    close_decimal(r[0], era5pl['surf_' + gc], 0)
+    close_decimal(r[1], era5pl['surf_' + gi], 0)
+
+
+@pytest.mark.parametrize('output_var,n', [('all', 8), ('srh', 2)])
+def test_srh_sigma_goldens(core, soundings, output_var, n):
+    r = core.calc_srh(*snd_srh_args(soundings), depth=3000, vertical_lev='sigma', output_var=output_var, method='cuda')
+    assert len(r) == n
+    close_decimal(r[0], soundings['SRH03_model_lev_rm'], 5)
+    close_decimal(r[1], soundings['SRH03_model_lev_lm'], 5)
+
+
+@pytest.mark.parametrize('output_var,n', [('all', 8), ('srh', 2)])
+def test_srh_pressure_goldens(core, era5pl, output_var, n):
+    r = core.calc_srh(*era_srh_args(era5pl), depth=3000, vertical_lev='pressure', output_var=output_var, method='cuda')
+    assert len(r) == n
+    close_decimal(r[0], era5pl['surf_srh_rm'], 5)
+    close_decimal(r[1], era5pl['surf_srh_lm'], 5)
+
+
+def test_stdheight_golden(soundings):
+    from xcape_b200.stdheight_cuda import stdheight
+    a = snd_cape_args(soundings)
+    H, Hs = stdheight(a[0].T, a[1].T, a[2].T, a[3], a[4], a[5], 0, 1, 2., 1)
+    ref = soundings['AGLH_model_lev']
+    assert np.nanmax(np.abs(np.asarray(H).T - ref[:, 1:])) < 1e-7
+    assert np.array_equal(Hs, ref[:, 0])
+
+
+# ------------------------------------------------------------------ oracle, synthetic
+@pytest.mark.parametrize('source', SOURCES)
+@pytest.mark.parametrize('adiabat', ADIABATS)
+def test_c1_model_levels_bitexact(core, oracle_mod, source, adiabat):
+    """BASELINE config 1: 1000 columns x 50 sigma levels; every source x adiabat."""
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C1', active=False)       # global mix: ~45 % of columns gated by ts <= 0
+    args = (d['p'], d['t'], d['td'], d['ps'], d['ts'], d['tds'])
+    kw = dict(source=source, ml_depth=500., adiabat=adiabat, pinc=500., vertical_lev='sigma')
+    got = core.calc_cape(*args, method='cuda', **kw)
+    ref = oracle_mod.calc_cape_ref(*args, tmode=oracle_mod.SPEC, **kw)
+    assert_bitexact(got, ref, f'C1 {source} {adiabat}')
+    libm = oracle_mod.calc_cape_ref(*args, tmode=oracle_mod.LIBM, **kw)
+    assert tol_ok(got[0], libm[0]).mean() > 0.999 and tol_ok(got[1], libm[1]).mean() > 0.999
+
+
+@pytest.mark.parametrize('source,ml_depth', [('surface', 500.), ('most-unstable', 500.), ('mixed-layer', 300.)])
+@pytest.mark.parametrize('shuffle', [False, True])
+def test_c2_shape_pressure_levels_bitexact(core, oracle_mod, source, ml_depth, shuffle):
+    """BASELINE config 2 shape (ERA5 37 pressure levels), 30 000-column sample, incl. status words."""
+    from xcape_b200.cape_cuda import cape as cape_cuda
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C2', cols=(100_000, 130_000), shuffle=shuffle)
+    args = (d['p'], d['t'], d['td'], d['ps'], d['ts'], d['tds'])
+    kw = dict(source=source, ml_depth=ml_depth, adiabat='pseudo-liquid', pinc=500., vertical_lev='pressure')
+    got = core.calc_cape(*args, method='cuda', **kw)
+    res, cnt = oracle_mod.calc_cape_ref(*args, tmode=oracle_mod.SPEC, counters=True, nthreads=8, **kw)
+    assert_bitexact(got, res, f'C2 {source}')
+    src = {'surface': 1, 'most-unstable': 2, 'mixed-layer': 3}[source]
+    out = cape_cuda(d['p'], d['t'].T, d['td'].T, d['ps'], d['ts'], d['tds'], 1, None, src, ml_depth, 1, 500., 2,
+                    return_counters=True)
+    assert np.array_equal(out[4], cnt['status'])
+    assert np.array_equal(out[5], cnt['n_iter'])        # the roofline work counter is the oracle's
+    # against the arithmetic gfortran would produce (glibc libm): the stated tolerance
+    libm = oracle_mod.calc_cape_ref(*args, tmode=oracle_mod.LIBM, nthreads=8, **kw)
+    ok = tol_ok(got[0], libm[0]) & tol_ok(got[1], libm[1])
+    assert ok.mean() >= 0.9995, f'{(~ok).sum()} columns outside max(1, 1e-4 rel) vs libm oracle'
+    if source == 'most-unstable':
+        assert (np.asarray(got[2]) != libm[2]).mean() < 1e-3
+
+
+def test_c5_shape_137_levels_bitexact(core, oracle_mod):
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C5', cols=(0, 6000))
+    args = (d['p'], d['t'], d['td'], d['ps'], d['ts'], d['tds'])
+    kw = dict(source='most-unstable', adiabat='pseudo-liquid', pinc=500., vertical_lev='sigma')
+    got = core.calc_cape(*args, method='cuda', **kw)
+    ref = oracle_mod.calc_cape_ref(*args, tmode=oracle_mod.SPEC, nthreads=8, **kw)
+    assert_bitexact(got, ref, 'C5 MU')
+
+
+@pytest.mark.parametrize('pinc', [100., 1000., 2500., 30000.])
+def test_pinc_sweep(core, oracle_mod, pinc):
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C2', cols=(0, 3000))
+    args = (d['p'], d['t'], d['td'], d['ps'], d['ts'], d['tds'])
+    kw = dict(source='surface', adiabat='pseudo-liquid', pinc=pinc, vertical_lev='pressure')
+    assert_bitexact(core.calc_cape(*args, method='cuda', **kw),
+                    oracle_mod.calc_cape_ref(*args, tmode=oracle_mod.SPEC, nthreads=8, **kw), f'pinc {pinc}')
+
+
+# ------------------------------------------------------------------ layouts / dtypes / memory spaces
+def test_layouts_dtypes_and_device_tensors_agree(core):
+    import torch
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C3', cols=(0, 5000 + 37))            # ragged: not a multiple of the CTA width
+    base = core.calc_cape(d['p'], d['t'], d['td'], d['ps'], d['ts'], d['tds'], source='most-unstable', pinc=500.,
+                          vertical_lev='sigma', method='cuda')
+    # float64 inputs: the device down-casts exactly like f2py
+    f64 = core.calc_cape(*(d[k].astype(np.float64) for k in ('p', 't', 'td', 'ps', 'ts', 'tds')),
+                         source='most-unstable', pinc=500., vertical_lev='sigma', method='cuda')
+    # level-major (lev_axis=0) zero-copy path
+    lm = core.calc_cape(np.ascontiguousarray(d['p'].T), np.ascontiguousarray(d['t'].T), np.ascontiguousarray(d['td'].T),
+                        d['ps'], d['ts'], d['tds'], source='most-unstable', pinc=500., vertical_lev='sigma',
+                        method='cuda', lev_axis=0)
+    # CUDA tensors in -> CUDA tensors out
+    dev = core.calc_cape(*(torch.from_numpy(d[k]).cuda() for k in ('p', 't', 'td', 'ps', 'ts', 'tds')),
+                         source='most-unstable', pinc=500., vertical_lev='sigma', method='cuda')
+    assert all(x.is_cuda for x in dev)
+    devlm = core.calc_cape(*(torch.from_numpy(np.ascontiguousarray(d[k].T)).cuda() for k in ('p', 't', 'td')),
+                           *(torch.from_numpy(d[k]).cuda() for k in ('ps', 'ts', 'tds')),
+                           source='most-unstable', pinc=500., vertical_lev='sigma', method='cuda', lev_axis=0)
+    torch.cuda.synchronize()
+    for other, name in ((f64, 'f64'), (lm, 'level-major'), ([x.cpu().numpy() for x in dev], 'device'),
+                        ([x.cpu().numpy() for x in devlm], 'device level-major')):
+        assert_bitexact(other, base, name)
+
+
+def test_nd_grid_shapes(core):
+    """(ny, nx, nlev) inputs -> (ny, nx) outputs; 2 vs 4 returns (reference test_calc_cape_shape_3d)."""
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C1')
+    g = (25, 40)
+    r = core.calc_cape(d['p'].reshape(g + (50,)), d['t'].reshape(g + (50,)), d['td'].reshape(g + (50,)),
+                       d['ps'].reshape(g), d['ts'].reshape(g), d['tds'].reshape(g), source='surface',
+                       vertical_lev='sigma', method='cuda')
+    assert len(r) == 2 and all(x.shape == g for x in r)
+    flat = core.calc_cape(d['p'], d['t'], d['td'], d['ps'], d['ts'], d['tds'], source='surface', vertical_lev='sigma',
+                          method='cuda')
+    assert np.array_equal(r[0].ravel(), flat[0])
+    # single column, 1-D inputs
+    one = core.calc_cape(d['p'][3], d['t'][3], d['td'][3], d['ps'][3], d['ts'][3], d['tds'][3], source='most-unstable',
+                         vertical_lev='sigma', method='cuda')
+    assert len(one) == 4 and all(x.shape == (1,) for x in one) and one[0][0] == flat[0][3]
+
+
+def test_pres_lev_pos_matches_numpy(core, oracle_mod):
+    from xcape_b200.cape_cuda import pres_lev_pos
+    from xcape_b200.synthetic import ERA5_LEVELS_HPA
+    rng = np.random.default_rng(3)
+    ps = rng.uniform(480, 1080, 20000)
+    ps[:40] = np.repeat(ERA5_LEVELS_HPA[:20].astype(np.float64), 2)     # exact ties p == ps are kept (B-9)
+    ps[40] = 2000.0; ps[41] = 0.5                                       # all levels used / all levels masked -> 1
+    for dt in (np.float64, np.float32):
+        ref = oracle_mod.pres_lev_pos(ps.astype(dt), ERA5_LEVELS_HPA.astype(dt)[:, None])
+        got = pres_lev_pos(ERA5_LEVELS_HPA.astype(dt), ps.astype(dt))
+        assert np.array_equal(got, ref.astype(np.int32))
+    assert got[41] == 1
+
+
+# ------------------------------------------------------------------ edge cases
+def test_empty_input(core):
+    z = np.zeros((0, 37), np.float32); s = np.zeros((0,), np.float32)
+    r = core.calc_cape(np.linspace(1000, 1, 37).astype(np.float32), z, z, s, s, s, source='most-unstable',
+                       vertical_lev='pressure', method='cuda')
+    assert len(r) == 4 and all(x.shape == (0,) for x in r)
+
+
+def test_gate_nonconvergence_and_high_surface(core, oracle_mod):
+    """ts <= 0 gate, NaN ts, the reference's non-convergence branch (hot, near-saturated
+    parcels: cape = cin = 0), MU with the surface above 500 hPa (MUlvl stays -999999)."""
+    from xcape_b200.cape_cuda import cape as cape_cuda
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C1', cols=(0, 512))
+    p, t, td, ps, ts, tds = (d[k].copy() for k in ('p', 't', 'td', 'ps', 'ts', 'tds'))
+    ts[0] = 0.0; ts[1] = -3.0; ts[2] = np.nan
+    ts[8:72] = np.linspace(33.0, 38.0, 64); tds[8:72] = ts[8:72] - np.linspace(0.2, 2.0, 64)   # extreme parcels
+    t[8:72, 0] = ts[8:72] - 0.5; td[8:72, 0] = tds[8:72] - 0.5
+    ps[100:110] = 480.0; p[100:110] = (480.0 * np.linspace(0.99, 0.02, 50)).astype(np.float32)   # surface above 500 hPa
+    for source in ('surface', 'most-unstable', 'mixed-layer'):
+        src = {'surface': 1, 'most-unstable': 2, 'mixed-layer': 3}[source]
+        got = cape_cuda(p.T, t.T, td.T, ps, ts, tds, 0, 1, src, 500., 1, 500., 1, return_status=True)
+        (ref, cnt) = oracle_mod.calc_cape_ref(p, t, td, ps, ts, tds, source=source, pinc=500., vertical_lev='sigma',
+                                              tmode=oracle_mod.SPEC, counters=True)
+        assert_bitexact(got[:4], ref, f'edge {source}')
+        assert np.array_equal(got[4], cnt['status'])
+        assert (got[4][:3] == 1).all() and (got[0][:3] == 0).all() and (got[2][:3] == 0).all()
+    assert (cnt['status'] == 2).sum() > 0, 'edge set should hit the non-convergence branch'
+    mu = cape_cuda(p.T, t.T, td.T, ps, ts, tds, 0, 1, 2, 500., 1, 500., 1)
+    assert (mu[2][100:110] == -999999).all()
+
+
+@pytest.mark.parametrize('ml_depth', [5.0, 300.0, 60000.0])
+def test_mixed_layer_depth_cases(core, oracle_mod, ml_depth):
+    """ML cases of CAPE_CODE_model_lev.f90:286-339: second level above the layer / interior /
+    whole column inside the layer (kmax = nk -> no ascent, zeros)."""
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C1')
+    args = (d['p'], d['t'], d['td'], d['ps'], d['ts'], d['tds'])
+    kw = dict(source='mixed-layer', ml_depth=ml_depth, pinc=500., vertical_lev='sigma')
+    got = core.calc_cape(*args, method='cuda', **kw)
+    ref = oracle_mod.calc_cape_ref(*args, tmode=oracle_mod.SPEC, **kw)
+    assert_bitexact(got, ref, f'ml_depth {ml_depth}')
+    if ml_depth > 50000:
+        assert (got[0] == 0).all() and (got[1] == 0).all()
+
+
+def test_bad_arguments_raise(core):
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C1', cols=(0, 64))
+    args = (d['p'], d['t'], d['td'], d['ps'], d['ts'], d['tds'])
+    with pytest.raises(ValueError):
+        core.calc_cape(*args, pinc=0.0, vertical_lev='sigma', method='cuda')
+    with pytest.raises(KeyError):
+        core.calc_cape(*args, source='bogus', vertical_lev='sigma', method='cuda')
+    with pytest.raises(ValueError):
+        core.calc_cape(*args, vertical_lev='pressure', method='cuda')          # "P should be 1d"
+    with pytest.raises(ValueError):
+        core.calc_cape(*args[:5], vertical_lev='sigma', method='cuda')
+
+
+# ------------------------------------------------------------------ SRH vs oracle
+@pytest.mark.parametrize('cfg,vertical_lev', [('C3', 'sigma'), ('C2', 'pressure')])
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_srh_vs_oracle(core, oracle_mod, cfg, vertical_lev, dtype):
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings(cfg, cols=(0, 20000))
+    args = tuple(d[k].astype(dtype) for k in ('p', 't', 'td', 'u', 'v', 'ps', 'ts', 'tds', 'us', 'vs'))
+    for depth in (1000, 3000):
+        got = core.calc_srh(*args, depth=depth, vertical_lev=vertical_lev, output_var='all', method='cuda')
+        ref = oracle_mod.calc_srh_ref(*args, depth=depth, vertical_lev=vertical_lev, output_var='all', nthreads=8)
+        assert got[0].dtype == np.float64 and got[2].dtype == np.float32
+        for g, r in zip(got[:2], ref[:2]):
+            assert np.abs(g - r).max() <= 1e-6, np.abs(g - r).max()          # far inside max(1, 1e-4 rel)
+        for g, r in zip(got[2:], ref[2:]):
+            assert np.abs(g - r).max() <= 2e-5, np.abs(g - r).max()
+
+
+def test_srh_nonmonotone_pressure_takes_exact_path(core, oracle_mod):
+    """Duplicate / out-of-order pressure levels: the kernel's EXACT path must reproduce
+    DINTERP2DZ's top-down 'highest bracket wins' search literally."""
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C3', cols=(0, 2048))
+    p = d['p'].copy()
+    p[::3, 7] = p[::3, 6]                       # duplicate level (dp = 0), as in the soundings fixture
+    p[1::7, 12] = p[1::7, 10] + 1.0             # a level out of order -> heights not monotone
+    args = (p, d['t'], d['td'], d['u'], d['v'], d['ps'], d['ts'], d['tds'], d['us'], d['vs'])
+    got = core.calc_srh(*args, depth=3000, vertical_lev='sigma', output_var='all', method='cuda')
+    ref = oracle_mod.calc_srh_ref(*args, depth=3000, vertical_lev='sigma', output_var='all')
+    for g, r in zip(got[:2], ref[:2]):
+        assert np.abs(g - r).max() <= 1e-6
+    for g, r in zip(got[2:], ref[2:]):
+        assert np.abs(g - r).max() <= 2e-5
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_era5_field_properties(core):
+    """BASELINE config 2 at full size (721 x 1440 x 37, most-unstable): size-independent
+    properties — block-split invariance (a column's result does not depend on its neighbours
+    or on the launch geometry), permutation equivariance, gate semantics, index ranges."""
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C2', active=False)
+    ncol = d['t'].shape[0]
+    assert ncol == 721 * 1440
+    kw = dict(source='most-unstable', pinc=500., vertical_lev='pressure', method='cuda')
+    full = core.calc_cape(d['p'], d['t'], d['td'], d['ps'], d['ts'], d['tds'], **kw)
+    cape, cin, mu, z = full
+    gated = ~(d['ts'] > 0)
+    assert gated.any() and (cape[gated] == 0).all() and (mu[gated] == 0).all() and (z[gated] == 0).all()
+    live = ~gated
+    assert (cape >= 0).all() and (cin >= 0).all() and np.isfinite(cape).all() and np.isfinite(cin).all()
+    assert ((mu[live] >= 1) & (mu[live] <= 38)).all()
+    # a permuted copy of 50 000 columns gives the permuted results
+    rng = np.random.default_rng(11)
+    idx = rng.choice(ncol, 50_000, replace=False)
+    sub = core.calc_cape(d['p'], d['t'][idx], d['td'][idx], d['ps'][idx], d['ts'][idx], d['tds'][idx], **kw)
+    for a, b in zip(sub, full):
+        assert np.array_equal(a, b[idx])
+    # checksum of checksums: two halves computed separately == whole
+    h = ncol // 2 + 13
+    a = core.calc_cape(d['p'], d['t'][:h], d['td'][:h], d['ps'][:h], d['ts'][:h], d['tds'][:h], **kw)
+    b = core.calc_cape(d['p'], d['t'][h:], d['td'][h:], d['ps'][h:], d['ts'][h:], d['tds'][h:], **kw)
+    assert np.float64(a[0].astype(np.float64).sum() + b[0].astype(np.float64).sum()) == cape.astype(np.float64).sum()
+    assert np.array_equal(np.concatenate([a[2], b[2]]), mu)

@@ -1,0 +1,106 @@
+"""Host-side logic that needs no GPU: argument validation and reshaping in xcape_b200.core
+(mirrors reference test/test_core.py:39-58 with method='dummy'), array/layout plumbing,
+column sharding, the synthetic generator."""
+import numpy as np
+import pytest
+
+from xcape_b200 import _array as A
+from xcape_b200 import _lib, core
+from xcape_b200.sharding import column_blocks, rank_block
+from xcape_b200.synthetic import CONFIGS, make_soundings
+
+
+@pytest.mark.parametrize('source,n_returns', [('surface', 2), ('most-unstable', 4)])
+@pytest.mark.parametrize('vertical_lev', ['sigma', 'pressure'])
+def test_calc_cape_shape_3d_dummy(source, n_returns, vertical_lev):
+    rng = np.random.default_rng(0)
+    p, t, td = (rng.random((5, 10, 20)) for _ in range(3))
+    ps, ts, tds = (rng.random((5, 10)) for _ in range(3))
+    args = (p, t, td, ps, ts, tds) if vertical_lev == 'sigma' else (np.ones(20), t, td, ps, ts, tds)
+    if vertical_lev == 'pressure':
+        # the dummy backend asserts p.ndim == 2 (core.py:116) and gets p as (nlev, 1)
+        pass
+    result = core.calc_cape(*args, source=source, vertical_lev=vertical_lev, method='dummy')
+    assert len(result) == n_returns
+    for r in result:
+        assert r.shape == p.shape[:-1]
+
+
+def test_argument_errors():
+    rng = np.random.default_rng(0)
+    p, t, td = (rng.random((4, 6, 9)) for _ in range(3))
+    ps, ts, tds = (rng.random((4, 6)) for _ in range(3))
+    with pytest.raises(ValueError, match='Too few'):
+        core.calc_cape(p, t, td, ps, ts, vertical_lev='sigma', method='dummy')
+    with pytest.raises(ValueError, match='Too many'):
+        core.calc_cape(p, t, td, ps, ts, tds, tds, vertical_lev='sigma', method='dummy')
+    with pytest.raises(ValueError, match='vertical_lev'):
+        core.calc_cape(p, t, td, ps, ts, tds, vertical_lev='eta', method='dummy')
+    with pytest.raises(ValueError, match='P should be 1d'):
+        core.calc_cape(p, t, td, ps, ts, tds, vertical_lev='pressure', method='dummy')
+    with pytest.raises(ValueError, match='same shape'):
+        core.calc_cape(p, t[:, :, :8], td, ps, ts, tds, vertical_lev='sigma', method='dummy')
+    with pytest.raises(ValueError, match='same shape'):
+        core.calc_cape(p, t, td, ps, ts[:3], tds, vertical_lev='sigma', method='dummy')
+    with pytest.raises(ValueError, match='invalid method'):
+        core.calc_cape(p, t, td, ps, ts, tds, vertical_lev='sigma', method='numba')
+    with pytest.raises(KeyError):
+        core.calc_cape(p, t, td, ps, ts, tds, vertical_lev='sigma', source='nope', method='dummy')
+    with pytest.raises(KeyError):
+        core.calc_cape(p, t, td, ps, ts, tds, vertical_lev='sigma', adiabat='nope', method='dummy')
+    with pytest.raises(ValueError):
+        core.calc_srh(p, t, td, vertical_lev='sigma')
+    with pytest.raises(ImportError):
+        core.calc_cape(p, t, td, ps, ts, tds, vertical_lev='sigma', method='fortran')
+
+
+def test_columns_views_are_zero_copy_and_layouts():
+    t = np.arange(4 * 6 * 9, dtype=np.float32).reshape(4, 6, 9)
+    (t2,) = core._columns_2d([t], -1)
+    assert t2.shape == (9, 24) and np.shares_memory(t2, t)
+    assert A.layout_of_2d(t2) == _lib.LEVEL_LAST                 # reference layout: each column contiguous
+    tm = np.ascontiguousarray(np.moveaxis(t, -1, 0))
+    (t3,) = core._columns_2d([tm], 0)
+    assert t3.shape == (9, 24) and np.shares_memory(t3, tm)
+    assert A.layout_of_2d(t3) == _lib.LEVEL_MAJOR
+    assert np.array_equal(t2, t3)
+    assert A.layout_of_2d(t2[:, ::2]) is None
+    f3, f1, p, dt, layout, mem, _ = A.prepare_fields([t2, t2[::1]], [np.zeros(24)], p=np.zeros(9, np.float32))
+    assert dt == _lib.F64 and layout == _lib.LEVEL_LAST and mem == _lib.MEM_HOST     # mixed dtypes promote
+    f3, *_rest = A.prepare_fields([t2[:, ::2], t2[:, 1::2]], [np.zeros(12, np.float32)])
+    assert A.layout_of_2d(f3[0]) == _lib.LEVEL_LAST and _rest[2] == _lib.F32         # strided -> dense copy
+    assert core._grid_shape((9,), -1) == (1,) and core._grid_shape((4, 6, 9), -1) == (4, 6)
+    assert core._grid_shape((9, 4, 6), 0) == (4, 6)
+
+
+@pytest.mark.parametrize('ncol', [0, 1, 127, 128, 129, 1000, 721 * 1440, 24 * 721 * 1440])
+@pytest.mark.parametrize('n', [1, 2, 3, 4, 8])
+def test_column_blocks_partition(ncol, n):
+    blocks = column_blocks(ncol, n)
+    assert len(blocks) == n and blocks[0][0] == 0 and blocks[-1][1] == ncol
+    for (a0, a1), (b0, b1) in zip(blocks, blocks[1:]):
+        assert a1 == b0 and a0 <= a1
+    sizes = [b - a for a, b in blocks]
+    assert sum(sizes) == ncol and max(sizes) - min(sizes) <= 128 + 127
+    assert all(a % 128 == 0 for a, _ in blocks if a < ncol)
+    assert [rank_block(ncol, r, n) for r in range(n)] == blocks
+
+
+def test_synthetic_is_deterministic_and_shardable():
+    a = make_soundings('C2', cols=(3000, 9500))
+    b = make_soundings('C2', cols=(0, 12000))
+    for k in ('t', 'td', 'u', 'v', 'ps', 'ts', 'tds'):
+        assert a[k].dtype == np.float32
+        assert np.array_equal(a[k], b[k][3000:9500])
+    assert a['p'].shape == (37,) and a['t'].shape == (6500, 37)
+    c = make_soundings('C3', cols=(0, 100))
+    assert c['p'].shape == (100, 50) and (np.diff(c['p'], axis=1) < 0).all()
+    assert (a['tds'] <= 27.0).all() and (a['ts'] > 0).all() and (a['td'] <= a['t']).all()
+    mix = make_soundings('C2', cols=(0, 20000), active=False)
+    assert 0.2 < (mix['ts'] <= 0).mean() < 0.7
+    s = make_soundings('C1', shuffle=True)
+    u = make_soundings('C1')
+    assert not np.array_equal(s['ps'], u['ps'])
+    assert CONFIGS['C2']['grid'] == (721, 1440) and CONFIGS['C5']['nlev'] == 137
+    d5 = make_soundings('C5', cols=(0, 8))
+    assert d5['p'].shape == (8, 137) and d5['p'][:, -1].max() < 0.2

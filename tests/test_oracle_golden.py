@@ -1,0 +1,106 @@
+"""The oracle against every golden vector the reference's tests hold for the path
+(reference test/test_core.py:68-286).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import close_decimal, era_cape_args, era_srh_args, snd_cape_args, snd_srh_args
+
+TMODES = [0, 1, 2]  # LIBM, CR, SPEC
+
+
+@pytest.mark.parametrize('tmode', TMODES)
+@pytest.mark.parametrize('source,pinc,gc,gi', [
+    ('surface', 100, 'SB_CAPE_pinc100', 'SB_CIN_pinc100'),
+    ('mixed-layer', 1000, 'ML_CAPE_pinc1000_mldepth500', 'ML_CIN_pinc1000_mldepth500'),
+    ('most-unstable', 100, 'MU_CAPE_pinc100', 'MU_CIN_pinc100')])
+def test_cape_sigma_goldens(oracle_mod, soundings, tmode, source, pinc, gc, gi):
+    # test_core.py:68-116
+    r = oracle_mod.calc_cape_ref(*snd_cape_args(soundings), source=source, ml_depth=500., adiabat='pseudo-liquid',
+                                 pinc=pinc, vertical_lev='sigma', tmode=tmode)
+    close_decimal(r[0], soundings[gc], 0)
+    close_decimal(r[1], soundings[gi], 0)
+    # the survey's probe found these goldens are reproduced EXACTLY by a float32 restatement
+    assert np.array_equal(r[0], soundings[gc].astype(np.float32))
+    assert np.array_equal(r[1], soundings[gi].astype(np.float32))
+    if source == 'most-unstable':
+        assert np.array_equal(r[2], soundings['MU_lv_pinc100'].astype(np.int32))
+        assert np.array_equal(r[3], soundings['MU_z_pinc100'].astype(np.float32))
+
+
+@pytest.mark.parametrize('tmode', TMODES)
+@pytest.mark.parametrize('source,gc,gi', [('surface', 'capesp500', 'cinsp500'),
+                                          ('mixed-layer', 'capeml300p500', 'cinml300p500'),
+                                          ('most-unstable', 'capemup500', 'cinmup500')])
+def test_cape_pressure_goldens(oracle_mod, era5pl, tmode, source, gc, gi):
+    # test_core.py:120-170
+    r = oracle_mod.calc_cape_ref(*era_cape_args(era5pl), source=source, ml_depth=300, adiabat='pseudo-liquid',
+                                 pinc=500, vertical_lev='pressure', tmode=tmode)
+    close_decimal(r[0], era5pl['surf_' + gc], 0)
+    close_decimal(r[1], era5pl['surf_' + gi], 0)
+    assert np.abs(r[0] - era5pl['surf_' + gc]).max() < 2e-2
+    assert np.abs(r[1] - era5pl['surf_' + gi]).max() < 2e-2
+
+
+def test_pres_lev_pos_matches_fixture(oracle_mod, era5pl):
+    plp = oracle_mod.pres_lev_pos(era5pl['surf_p'], era5pl['level'][:, None])
+    assert set(np.unique(plp)) <= {2, 3}        # surface p ~ 968-979 hPa
+
+
+def test_srh_sigma_goldens(oracle_mod, soundings):
+    # test_core.py:173-229
+    r = oracle_mod.calc_srh_ref(*snd_srh_args(soundings), depth=3000, vertical_lev='sigma', output_var='all')
+    assert len(r) == 8
+    close_decimal(r[0], soundings['SRH03_model_lev_rm'], 5)
+    close_decimal(r[1], soundings['SRH03_model_lev_lm'], 5)
+
+
+def test_srh_pressure_goldens(oracle_mod, era5pl):
+    # test_core.py:231-286
+    r = oracle_mod.calc_srh_ref(*era_srh_args(era5pl), depth=3000, vertical_lev='pressure', output_var='srh')
+    close_decimal(r[0], era5pl['surf_srh_rm'], 5)
+    close_decimal(r[1], era5pl['surf_srh_lm'], 5)
+
+
+def test_stdheight_golden(oracle_mod, soundings):
+    # AGLH_model_lev is carried by the fixture (not asserted by the reference) — pins stdheight
+    a = snd_cape_args(soundings)
+    p2, t2, td2 = oracle_mod._to2d(a[0], a[1], a[2])
+    H, Hs = oracle_mod.stdheight(p2, t2, td2, a[3], a[4], a[5], 0, 1, 2., 1)
+    ref = soundings['AGLH_model_lev']
+    assert np.nanmax(np.abs(H.T - ref[:, 1:])) < 1e-9
+    assert np.array_equal(Hs, ref[:, 0])
+
+
+def test_spec_math_is_a_valid_libm(oracle_mod):
+    """SPEC exp/log/pow agree with the correctly-rounded binary32 result."""
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-45, 5, 500_000).astype(np.float32)
+    assert (oracle_mod.vec_math('exp', x, tmode=2) != oracle_mod.vec_math('exp', x, tmode=1)).mean() < 1e-4
+    x = rng.uniform(-0.05, 0.05, 500_000).astype(np.float32)
+    assert (oracle_mod.vec_math('exp', x, tmode=2) != oracle_mod.vec_math('exp', x, tmode=1)).mean() < 1e-4
+    x = np.exp(rng.uniform(-8, 8, 500_000)).astype(np.float32)
+    assert (oracle_mod.vec_math('log', x, tmode=2) != oracle_mod.vec_math('log', x, tmode=1)).mean() < 1e-4
+    x = rng.uniform(0.0005, 1.1, 500_000).astype(np.float32)
+    y = np.float32(287.04) / np.float32(1005.7)
+    assert (oracle_mod.vec_math('pow', x, y, tmode=2) != oracle_mod.vec_math('pow', x, y, tmode=1)).mean() < 1e-4
+    L = oracle_mod.lib()
+    assert L.xcape_ref_expf(-800.0, 2) == 0.0 and np.isinf(L.xcape_ref_expf(800.0, 2))
+    assert np.isnan(L.xcape_ref_expf(float('nan'), 2)) and np.isnan(L.xcape_ref_logf(-1.0, 2))
+    assert L.xcape_ref_logf(0.0, 2) == -np.inf
+
+
+def test_skip_and_status_counters(oracle_mod, soundings):
+    """ts <= 0 degC gate (CAPE_CODE_model_lev.f90:77): sounding #13 has Ts = -4.9 degC."""
+    (c, ci, lv, z), cnt = oracle_mod.calc_cape_ref(*snd_cape_args(soundings), source='most-unstable', pinc=100,
+                                                   vertical_lev='sigma', counters=True)
+    assert soundings['temperature'][12, 0] < 0
+    assert c[12] == 0 and ci[12] == 0 and lv[12] == 0 and z[12] == 0
+    assert cnt['status'][12] == 1 and cnt['n_iter'][12] == 0
+    assert (cnt['status'][:12] == 0).all() and (cnt['n_iter'][:12] > 100).all()
+
+
+def test_contracted_oracle_is_a_small_perturbation(oracle_mod, soundings):
+    a = oracle_mod.calc_cape_ref(*snd_cape_args(soundings), source='surface', pinc=100, vertical_lev='sigma')
+    b = oracle_mod.calc_cape_ref(*snd_cape_args(soundings), source='surface', pinc=100, vertical_lev='sigma',
+                                 contract=True)
+    assert np.abs(a[0] - b[0]).max() < 1.0

@@ -1,0 +1,419 @@
+// api.cu — the C ABI of libxcape_b200.so (include/xcape_b200.h): argument validation,
+// canonicalisation of dtype/layout on the device, kernel dispatch, and the host-pointer
+// path (column blocks staged H2D / computed / D2H on a ring of streams).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "xc_common.cuh"
+#include "relayout.cuh"
+#include "cape_kernel.cuh"
+#include "srh_launch.cuh"
+#include "peaks.cuh"
+
+namespace xc {
+
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launches{0};
+
+namespace {
+
+// Stream-ordered scratch: cudaMallocAsync / cudaFreeAsync on the call's stream, so the
+// device-pointer entry points never synchronise.
+struct Scratch {
+  cudaStream_t s;
+  std::vector<void*> ptrs;
+  explicit Scratch(cudaStream_t st) : s(st) {}
+  template <class T> cudaError_t alloc(T** p, size_t n) {
+    void* q = nullptr;
+    cudaError_t e = cudaMallocAsync(&q, std::max<size_t>(n, 1) * sizeof(T), s);
+    if (e == cudaSuccess) ptrs.push_back(q);
+    *p = (T*)q;
+    return e;
+  }
+  ~Scratch() { for (void* q : ptrs) cudaFreeAsync(q, s); }
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int check_common(int64_t ncol, int nlev, int dtype, int layout, int mem) {
+  if (ncol < 0) return fail(XCAPE_ERR_ARG, "ncol < 0");
+  if (nlev < 1) return fail(XCAPE_ERR_ARG, "nlev < 1");
+  if (dtype != XCAPE_F32 && dtype != XCAPE_F64) return fail(XCAPE_ERR_ARG, "dtype must be XCAPE_F32 or XCAPE_F64");
+  if (layout != XCAPE_LEVEL_LAST && layout != XCAPE_LEVEL_MAJOR) return fail(XCAPE_ERR_ARG, "bad layout");
+  if (mem != XCAPE_MEM_HOST && mem != XCAPE_MEM_DEVICE) return fail(XCAPE_ERR_ARG, "bad mem");
+  return XCAPE_OK;
+}
+
+// 3-D field (dtype, layout, leading dimension ld_in for level-major) -> level-major float32.
+// Zero-copy when already float32 level-major.
+int canon3d(const void* in, int dtype, int layout, int64_t ncol, int nlev, int64_t ld_in,
+            Scratch& sc, const float** out, int64_t* ld_out, cudaStream_t s) {
+  if (dtype == XCAPE_F32 && layout == XCAPE_LEVEL_MAJOR) { *out = (const float*)in; *ld_out = ld_in; return XCAPE_OK; }
+  float* buf;
+  XC_CUDA(sc.alloc(&buf, (size_t)ncol * nlev));
+  *out = buf; *ld_out = ncol;
+  if (layout == XCAPE_LEVEL_LAST) return launch_transpose_cast(in, dtype, buf, ncol, nlev, ncol, s);
+  if (ld_in == ncol) return launch_cast_copy(in, dtype, buf, ncol * nlev, s);
+  for (int k = 0; k < nlev; ++k) {   // strided level-major float64 (host-chunk path never produces this; kept for generality)
+    int rc = launch_cast_copy((const char*)in + (size_t)k * ld_in * esize(dtype), dtype, buf + (size_t)k * ncol, ncol, s);
+    if (rc) return rc;
+  }
+  return XCAPE_OK;
+}
+
+int canon1d(const void* in, int dtype, int64_t n, Scratch& sc, const float** out, cudaStream_t s) {
+  if (dtype == XCAPE_F32) { *out = (const float*)in; return XCAPE_OK; }
+  float* buf;
+  XC_CUDA(sc.alloc(&buf, (size_t)n));
+  *out = buf;
+  return launch_cast_copy(in, dtype, buf, n, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// CAPE, device pointers, asynchronous on stream s.  ld_in: level stride of level-major input.
+// ---------------------------------------------------------------------------------------
+int cape_device(const void* p, const void* t, const void* td, const void* ps, const void* ts, const void* tds,
+                int64_t ncol, int nlev, int p_is_1d, int dtype, int layout, int64_t ld_in,
+                int source, int adiabat, float ml_depth, float pinc, const int32_t* start_3d,
+                float* cape, float* cin, int32_t* mulev, float* zmulev, int32_t* status, int32_t* n_iter,
+                int precision, cudaStream_t s) {
+  if (ncol == 0) return XCAPE_OK;
+  Scratch sc(s);
+  CapeArgs a{};
+  int rc;
+  int64_t ld = ncol, ldp = ncol;
+  const float* q;
+  if ((rc = canon3d(t, dtype, layout, ncol, nlev, ld_in, sc, &q, &ld, s))) return rc; a.t = q;
+  int64_t ld2 = ncol;
+  if ((rc = canon3d(td, dtype, layout, ncol, nlev, ld_in, sc, &q, &ld2, s))) return rc; a.td = q;
+  if (p_is_1d) {
+    if ((rc = canon1d(p, dtype, nlev, sc, &q, s))) return rc; a.p = q;
+  } else {
+    if ((rc = canon3d(p, dtype, layout, ncol, nlev, ld_in, sc, &q, &ldp, s))) return rc; a.p = q;
+  }
+  if (ld2 != ld || (!p_is_1d && ldp != ld)) return fail(XCAPE_ERR_ARG, "internal: inconsistent leading dimensions");
+  if ((rc = canon1d(ps, dtype, ncol, sc, &q, s))) return rc; a.ps = q;
+  if ((rc = canon1d(ts, dtype, ncol, sc, &q, s))) return rc; a.ts = q;
+  if ((rc = canon1d(tds, dtype, ncol, sc, &q, s))) return rc; a.tds = q;
+  a.start = start_3d;
+  if (p_is_1d && !start_3d) {
+    int32_t* st;
+    XC_CUDA(sc.alloc(&st, (size_t)ncol));
+    if ((rc = launch_pres_lev_pos(p, ps, dtype, ncol, nlev, st, s))) return rc;   // in the inputs' own dtype
+    a.start = st;
+  }
+  a.ncol = ncol; a.ld = ld; a.nlev = nlev; a.pinc = pinc; a.ml_depth = ml_depth;
+  a.cape = cape; a.cin = cin; a.zout = zmulev; a.mulvl = mulev; a.status = status; a.n_iter = n_iter;
+  if (precision == XCAPE_FAITHFUL) return launch_cape_faithful(a, source, adiabat, p_is_1d != 0, s);
+  return fail(XCAPE_ERR_ARG, "unknown precision mode");
+}
+
+// ---------------------------------------------------------------------------------------
+// SRH / heights, device pointers, asynchronous on stream s.
+// ---------------------------------------------------------------------------------------
+// 3-D field -> level-major in its OWN dtype (the SRH chain consumes binary64 inputs as such:
+// stdheight and SREH are double-precision routines).
+int canon3d_same(const void* in, int dtype, int layout, int64_t ncol, int nlev, int64_t ld_in, Scratch& sc,
+                 const void** out, int64_t* ld_out, cudaStream_t s) {
+  if (layout == XCAPE_LEVEL_MAJOR) { *out = in; *ld_out = ld_in; return XCAPE_OK; }
+  char* buf;
+  XC_CUDA(sc.alloc(&buf, (size_t)ncol * nlev * esize(dtype)));
+  *out = buf; *ld_out = ncol;
+  return launch_transpose_same(in, dtype, buf, ncol, nlev, ncol, s);
+}
+
+template <class T>
+int srh_device_t(const void* p, const void* t, const void* td, const void* u, const void* v, const void* ps,
+                 const void* ts, const void* tds, const void* us, const void* vs, int64_t ncol, int nlev, int p_is_1d,
+                 int dtype, int layout, int64_t ld_in, double depth, double aglh0, const int32_t* start_3d,
+                 double* srh_rm, double* srh_lm, float* rm, float* lm, float* mean6, cudaStream_t s) {
+  Scratch sc(s);
+  SrhArgs<T> a{};
+  int rc;
+  const void* q;
+  int64_t ld = ncol, l2 = ncol;
+  if ((rc = canon3d_same(t, dtype, layout, ncol, nlev, ld_in, sc, &q, &ld, s))) return rc; a.t = (const T*)q;
+  if ((rc = canon3d_same(td, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.td = (const T*)q;
+  if ((rc = canon3d_same(u, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.u = (const T*)q;
+  if ((rc = canon3d_same(v, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.v = (const T*)q;
+  if (p_is_1d) a.p = (const T*)p;
+  else { if ((rc = canon3d_same(p, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.p = (const T*)q; }
+  a.ps = (const T*)ps; a.ts = (const T*)ts; a.tds = (const T*)tds; a.us = (const T*)us; a.vs = (const T*)vs;
+  a.start = start_3d;
+  if (p_is_1d && !start_3d) {
+    int32_t* st;
+    XC_CUDA(sc.alloc(&st, (size_t)ncol));
+    if ((rc = launch_pres_lev_pos(p, ps, dtype, ncol, nlev, st, s))) return rc;
+    a.start = st;
+  }
+  a.ncol = ncol; a.ld = ld; a.nlev = nlev; a.depth = depth; a.aglh0 = aglh0;
+  a.srh_rm = srh_rm; a.srh_lm = srh_lm; a.rm = rm; a.lm = lm; a.mean6 = mean6;
+  return launch_srh(a, p_is_1d != 0, s);
+}
+
+template <class T>
+int height_device_t(const void* p, const void* t, const void* td, const void* ps, const void* ts, const void* tds,
+                    int64_t ncol, int nlev, int p_is_1d, int dtype, int layout, int64_t ld_in, double aglh0,
+                    const int32_t* start_3d, double* h, double* hs, cudaStream_t s) {
+  Scratch sc(s);
+  HeightArgs<T> a{};
+  int rc;
+  const void* q;
+  int64_t ld = ncol, l2 = ncol;
+  if ((rc = canon3d_same(t, dtype, layout, ncol, nlev, ld_in, sc, &q, &ld, s))) return rc; a.t = (const T*)q;
+  if ((rc = canon3d_same(td, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.td = (const T*)q;
+  if (p_is_1d) a.p = (const T*)p;
+  else { if ((rc = canon3d_same(p, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.p = (const T*)q; }
+  a.ps = (const T*)ps; a.ts = (const T*)ts; a.tds = (const T*)tds;
+  a.start = start_3d;
+  if (p_is_1d && !start_3d) {
+    int32_t* st;
+    XC_CUDA(sc.alloc(&st, (size_t)ncol));
+    if ((rc = launch_pres_lev_pos(p, ps, dtype, ncol, nlev, st, s))) return rc;
+    a.start = st;
+  }
+  a.ncol = ncol; a.ld = ld; a.nlev = nlev; a.aglh0 = aglh0; a.h = h; a.hs = hs;
+  if (layout == XCAPE_LEVEL_LAST) { a.h_col_stride = nlev; a.h_lev_stride = 1; }
+  else { a.h_col_stride = 1; a.h_lev_stride = ncol; }
+  return launch_stdheight(a, p_is_1d != 0, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// Host-pointer plumbing: a ring of streams, each owning device buffers for one column block.
+// The block's inputs go H2D, the caller-supplied `launch` enqueues the device work, the
+// outputs come D2H — all stream-ordered, so blocks on different streams overlap copy and
+// compute.  Pageable host memory works (the driver stages it); pinned memory overlaps fully.
+// ---------------------------------------------------------------------------------------
+constexpr int kStreams = 3;
+constexpr int64_t kChunkCols = 1 << 18;
+
+struct HostIn3 { const void* host; };                    // [ncol][nlev] or [nlev][ncol], es bytes/element
+struct HostIn1 { const void* host; size_t es; };          // [ncol]
+struct HostOut { void* host; size_t bytes_per_col; int is3d; };   // per-column outputs (is3d: nlev*8 bytes per column, layout-aware)
+
+struct Block {
+  std::vector<void*> in3, in1, out;
+  void* p1d = nullptr;
+};
+
+cudaError_t h2d_field(void* dst, const void* src, int layout, int64_t ncol, int nlev, int64_t c0, int64_t n, size_t es,
+                      cudaStream_t s) {
+  if (layout == XCAPE_LEVEL_LAST)
+    return cudaMemcpyAsync(dst, (const char*)src + (size_t)c0 * nlev * es, (size_t)n * nlev * es, cudaMemcpyHostToDevice, s);
+  return cudaMemcpy2DAsync(dst, (size_t)n * es, (const char*)src + (size_t)c0 * es, (size_t)ncol * es, (size_t)n * es,
+                           (size_t)nlev, cudaMemcpyHostToDevice, s);
+}
+cudaError_t d2h_field(void* dst, const void* src, int layout, int64_t ncol, int nlev, int64_t c0, int64_t n, size_t es,
+                      cudaStream_t s) {
+  if (layout == XCAPE_LEVEL_LAST)
+    return cudaMemcpyAsync((char*)dst + (size_t)c0 * nlev * es, src, (size_t)n * nlev * es, cudaMemcpyDeviceToHost, s);
+  return cudaMemcpy2DAsync((char*)dst + (size_t)c0 * es, (size_t)ncol * es, src, (size_t)n * es, (size_t)n * es, (size_t)nlev,
+                           cudaMemcpyDeviceToHost, s);
+}
+
+template <class F>
+int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_host, const std::vector<HostIn3>& in3,
+               const std::vector<HostIn1>& in1, const std::vector<HostOut>& outs, F launch) {
+  const int64_t chunk = std::min<int64_t>(ncol, kChunkCols);
+  const int nstream = (int)std::min<int64_t>(kStreams, (ncol + chunk - 1) / chunk);
+  cudaStream_t st[kStreams] = {};
+  Block b[kStreams];
+  auto body = [&]() -> int {
+    for (int i = 0; i < nstream; ++i) {
+      XC_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+      for (size_t k = 0; k < in3.size(); ++k) { void* q; XC_CUDA(cudaMallocAsync(&q, (size_t)chunk * nlev * es, st[i])); b[i].in3.push_back(q); }
+      for (size_t k = 0; k < in1.size(); ++k) { void* q; XC_CUDA(cudaMallocAsync(&q, (size_t)chunk * in1[k].es, st[i])); b[i].in1.push_back(q); }
+      for (size_t k = 0; k < outs.size(); ++k) {
+        void* q; XC_CUDA(cudaMallocAsync(&q, (size_t)chunk * (outs[k].is3d ? (size_t)nlev * 8 : outs[k].bytes_per_col), st[i]));
+        b[i].out.push_back(q);
+      }
+      if (p1d_host) {
+        XC_CUDA(cudaMallocAsync(&b[i].p1d, (size_t)nlev * es, st[i]));
+        XC_CUDA(cudaMemcpyAsync(b[i].p1d, p1d_host, (size_t)nlev * es, cudaMemcpyHostToDevice, st[i]));
+      }
+    }
+    int i = 0;
+    for (int64_t c0 = 0; c0 < ncol; c0 += chunk, i = (i + 1) % nstream) {
+      const int64_t n = std::min<int64_t>(chunk, ncol - c0);
+      cudaStream_t s = st[i];
+      for (size_t k = 0; k < in3.size(); ++k) XC_CUDA(h2d_field(b[i].in3[k], in3[k].host, layout, ncol, nlev, c0, n, es, s));
+      for (size_t k = 0; k < in1.size(); ++k)
+        XC_CUDA(cudaMemcpyAsync(b[i].in1[k], (const char*)in1[k].host + (size_t)c0 * in1[k].es, (size_t)n * in1[k].es, cudaMemcpyHostToDevice, s));
+      int r = launch(b[i], n, s);
+      if (r) return r;
+      for (size_t k = 0; k < outs.size(); ++k) {
+        if (!outs[k].host) continue;
+        if (outs[k].is3d) XC_CUDA(d2h_field(outs[k].host, b[i].out[k], layout, ncol, nlev, c0, n, 8, s));
+        else XC_CUDA(cudaMemcpyAsync((char*)outs[k].host + (size_t)c0 * outs[k].bytes_per_col, b[i].out[k], (size_t)n * outs[k].bytes_per_col, cudaMemcpyDeviceToHost, s));
+      }
+    }
+    for (int k = 0; k < nstream; ++k) XC_CUDA(cudaStreamSynchronize(st[k]));
+    return XCAPE_OK;
+  };
+  int rc = body();
+  std::string keep = g_last_error;
+  for (int i = 0; i < nstream; ++i) {
+    if (!st[i]) continue;
+    for (void* q : b[i].in3) cudaFreeAsync(q, st[i]);
+    for (void* q : b[i].in1) cudaFreeAsync(q, st[i]);
+    for (void* q : b[i].out) cudaFreeAsync(q, st[i]);
+    if (b[i].p1d) cudaFreeAsync(b[i].p1d, st[i]);
+    cudaStreamSynchronize(st[i]);
+    cudaStreamDestroy(st[i]);
+  }
+  if (rc) { cudaGetLastError(); g_last_error = keep; }
+  return rc;
+}
+
+}  // namespace
+}  // namespace xc
+
+using namespace xc;
+
+extern "C" {
+
+const char* xcape_cuda_last_error(void) { return g_last_error.c_str(); }
+const char* xcape_cuda_version(void) { return "xcape_b200 0.1.0 sm_100a"; }
+int64_t xcape_cuda_kernel_launches(void) { return g_launches.load(); }
+int xcape_cuda_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return n;
+}
+
+int xcape_cuda_measure_peaks(int device, int reps, double* fp32_tflops, double* fp64_tflops) {
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(XCAPE_ERR_NODEV, "cudaSetDevice failed");
+  return measure_peaks(reps, fp32_tflops, fp64_tflops);
+}
+
+int xcape_cuda_pres_lev_pos(const void* p, const void* ps, int64_t ncol, int nlev, int dtype, int mem,
+                            int32_t* start_3d, int device, void* stream) {
+  int rc = check_common(ncol, nlev, dtype, XCAPE_LEVEL_LAST, mem);
+  if (rc) return rc;
+  if (ncol == 0) return XCAPE_OK;
+  if (!p || !ps || !start_3d) return fail(XCAPE_ERR_ARG, "null pointer");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(XCAPE_ERR_NODEV, "cudaSetDevice failed");
+  if (mem == XCAPE_MEM_DEVICE) return launch_pres_lev_pos(p, ps, dtype, ncol, nlev, start_3d, (cudaStream_t)stream);
+  return run_staged(ncol, nlev, XCAPE_LEVEL_LAST, esize(dtype), p, {}, {{ps, esize(dtype)}}, {{start_3d, 4, 0}},
+                    [&](Block& b, int64_t n, cudaStream_t s) {
+                      return launch_pres_lev_pos(b.p1d, b.in1[0], dtype, n, nlev, (int32_t*)b.out[0], s);
+                    });
+}
+
+int xcape_cuda_cape(const void* p, const void* t, const void* td, const void* ps, const void* ts, const void* tds,
+                    int64_t ncol, int nlev, int p_is_1d, int dtype, int layout, int mem,
+                    int source, int adiabat, float ml_depth, float pinc, const int32_t* start_3d,
+                    float* cape, float* cin, int32_t* mulev, float* zmulev, int32_t* status, int32_t* n_iter,
+                    int precision, int device, void* stream) {
+  int rc = check_common(ncol, nlev, dtype, layout, mem);
+  if (rc) return rc;
+  if (source < 1 || source > 3) return fail(XCAPE_ERR_ARG, "source must be 1 (surface), 2 (most-unstable) or 3 (mixed-layer)");
+  if (adiabat < 1 || adiabat > 4) return fail(XCAPE_ERR_ARG, "adiabat must be 1..4");
+  if (!(pinc > 0.0f)) return fail(XCAPE_ERR_ARG, "pinc must be > 0");
+  if (precision != XCAPE_FAITHFUL) return fail(XCAPE_ERR_ARG, "unknown precision mode");
+  if (ncol == 0) return XCAPE_OK;
+  if (!p || !t || !td || !ps || !ts || !tds || !cape || !cin || !mulev || !zmulev) return fail(XCAPE_ERR_ARG, "null pointer");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(XCAPE_ERR_NODEV, "cudaSetDevice failed");
+
+  if (mem == XCAPE_MEM_DEVICE)
+    return cape_device(p, t, td, ps, ts, tds, ncol, nlev, p_is_1d, dtype, layout, ncol, source, adiabat, ml_depth, pinc,
+                       start_3d, cape, cin, mulev, zmulev, status, n_iter, precision, (cudaStream_t)stream);
+
+  const size_t es = esize(dtype);
+  std::vector<HostIn3> in3 = {{t}, {td}};
+  if (!p_is_1d) in3.push_back({p});
+  std::vector<HostIn1> in1 = {{ps, es}, {ts, es}, {tds, es}};
+  if (start_3d) in1.push_back({start_3d, 4});
+  std::vector<HostOut> outs = {{cape, 4, 0}, {cin, 4, 0}, {mulev, 4, 0}, {zmulev, 4, 0}, {status, 4, 0}, {n_iter, 4, 0}};
+  return run_staged(ncol, nlev, layout, es, p_is_1d ? p : nullptr, in3, in1, outs,
+                    [&](Block& b, int64_t n, cudaStream_t s) {
+                      return cape_device(p_is_1d ? b.p1d : b.in3[2], b.in3[0], b.in3[1], b.in1[0], b.in1[1], b.in1[2], n, nlev,
+                                         p_is_1d, dtype, layout, n, source, adiabat, ml_depth, pinc,
+                                         start_3d ? (const int32_t*)b.in1[3] : nullptr, (float*)b.out[0], (float*)b.out[1],
+                                         (int32_t*)b.out[2], (float*)b.out[3], status ? (int32_t*)b.out[4] : nullptr,
+                                         n_iter ? (int32_t*)b.out[5] : nullptr, precision, s);
+                    });
+}
+
+int xcape_cuda_srh(const void* p, const void* t, const void* td, const void* u, const void* v,
+                   const void* ps, const void* ts, const void* tds, const void* us, const void* vs,
+                   int64_t ncol, int nlev, int p_is_1d, int dtype, int layout, int mem,
+                   double depth, double aglh0, const int32_t* start_3d,
+                   double* srh_rm, double* srh_lm, float* rm, float* lm, float* mean6,
+                   int precision, int device, void* stream) {
+  int rc = check_common(ncol, nlev, dtype, layout, mem);
+  if (rc) return rc;
+  if (precision != XCAPE_FAITHFUL) return fail(XCAPE_ERR_ARG, "unknown precision mode");
+  if (ncol == 0) return XCAPE_OK;
+  if (!p || !t || !td || !u || !v || !ps || !ts || !tds || !us || !vs || !srh_rm || !srh_lm) return fail(XCAPE_ERR_ARG, "null pointer");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(XCAPE_ERR_NODEV, "cudaSetDevice failed");
+  auto dev = [&](const void* p_, const void* t_, const void* td_, const void* u_, const void* v_, const void* ps_,
+                 const void* ts_, const void* tds_, const void* us_, const void* vs_, int64_t n, int64_t ld_in,
+                 const int32_t* st_, double* srm_, double* slm_, float* rm_, float* lm_, float* m6_, cudaStream_t s) {
+    if (dtype == XCAPE_F64)
+      return srh_device_t<double>(p_, t_, td_, u_, v_, ps_, ts_, tds_, us_, vs_, n, nlev, p_is_1d, dtype, layout, ld_in, depth,
+                                  aglh0, st_, srm_, slm_, rm_, lm_, m6_, s);
+    return srh_device_t<float>(p_, t_, td_, u_, v_, ps_, ts_, tds_, us_, vs_, n, nlev, p_is_1d, dtype, layout, ld_in, depth,
+                               aglh0, st_, srm_, slm_, rm_, lm_, m6_, s);
+  };
+  if (mem == XCAPE_MEM_DEVICE)
+    return dev(p, t, td, u, v, ps, ts, tds, us, vs, ncol, ncol, start_3d, srh_rm, srh_lm, rm, lm, mean6, (cudaStream_t)stream);
+
+  const size_t es = esize(dtype);
+  std::vector<HostIn3> in3 = {{t}, {td}, {u}, {v}};
+  if (!p_is_1d) in3.push_back({p});
+  std::vector<HostIn1> in1 = {{ps, es}, {ts, es}, {tds, es}, {us, es}, {vs, es}};
+  if (start_3d) in1.push_back({start_3d, 4});
+  std::vector<HostOut> outs = {{srh_rm, 8, 0}, {srh_lm, 8, 0}, {rm, 8, 0}, {lm, 8, 0}, {mean6, 8, 0}};
+  return run_staged(ncol, nlev, layout, es, p_is_1d ? p : nullptr, in3, in1, outs,
+                    [&](Block& b, int64_t n, cudaStream_t s) {
+                      return dev(p_is_1d ? b.p1d : b.in3[4], b.in3[0], b.in3[1], b.in3[2], b.in3[3], b.in1[0], b.in1[1],
+                                 b.in1[2], b.in1[3], b.in1[4], n, n, start_3d ? (const int32_t*)b.in1[5] : nullptr,
+                                 (double*)b.out[0], (double*)b.out[1], rm ? (float*)b.out[2] : nullptr,
+                                 lm ? (float*)b.out[3] : nullptr, mean6 ? (float*)b.out[4] : nullptr, s);
+                    });
+}
+
+int xcape_cuda_stdheight(const void* p, const void* t, const void* td, const void* ps, const void* ts, const void* tds,
+                         int64_t ncol, int nlev, int p_is_1d, int dtype, int layout, int mem, double aglh0,
+                         const int32_t* start_3d, double* h, double* hs, int device, void* stream) {
+  int rc = check_common(ncol, nlev, dtype, layout, mem);
+  if (rc) return rc;
+  if (ncol == 0) return XCAPE_OK;
+  if (!p || !t || !td || !ps || !ts || !tds || !h || !hs) return fail(XCAPE_ERR_ARG, "null pointer");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(XCAPE_ERR_NODEV, "cudaSetDevice failed");
+  auto dev = [&](const void* p_, const void* t_, const void* td_, const void* ps_, const void* ts_, const void* tds_,
+                 int64_t n, const int32_t* st_, double* h_, double* hs_, cudaStream_t s) {
+    if (dtype == XCAPE_F64)
+      return height_device_t<double>(p_, t_, td_, ps_, ts_, tds_, n, nlev, p_is_1d, dtype, layout, n, aglh0, st_, h_, hs_, s);
+    return height_device_t<float>(p_, t_, td_, ps_, ts_, tds_, n, nlev, p_is_1d, dtype, layout, n, aglh0, st_, h_, hs_, s);
+  };
+  if (mem == XCAPE_MEM_DEVICE) return dev(p, t, td, ps, ts, tds, ncol, start_3d, h, hs, (cudaStream_t)stream);
+  const size_t es = esize(dtype);
+  std::vector<HostIn3> in3 = {{t}, {td}};
+  if (!p_is_1d) in3.push_back({p});
+  std::vector<HostIn1> in1 = {{ps, es}, {ts, es}, {tds, es}};
+  if (start_3d) in1.push_back({start_3d, 4});
+  std::vector<HostOut> outs = {{h, 0, 1}, {hs, 8, 0}};
+  return run_staged(ncol, nlev, layout, es, p_is_1d ? p : nullptr, in3, in1, outs,
+                    [&](Block& b, int64_t n, cudaStream_t s) {
+                      return dev(p_is_1d ? b.p1d : b.in3[2], b.in3[0], b.in3[1], b.in1[0], b.in1[1], b.in1[2], n,
+                                 start_3d ? (const int32_t*)b.in1[3] : nullptr, (double*)b.out[0], (double*)b.out[1], s);
+                    });
+}
+
+}  // extern "C"

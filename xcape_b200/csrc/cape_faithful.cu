@@ -1,0 +1,47 @@
+// cape_faithful.cu — instantiations of the CAPE kernel with the FAITHFUL math policy.
+// Compiled with -fmad=false -prec-div=true -prec-sqrt=true -ftz=false: every binary32
+// operation is an individually rounded IEEE operation, exactly like the reference built by
+// gfortran -O3 on x86-64 (no FMA contraction).
+#include "xc_common.cuh"
+#include "xc_math_spec.cuh"
+#include "cape_kernel.cuh"
+
+namespace xc {
+
+struct MathSpec {
+  static __device__ __forceinline__ float exp(float x) { return spec_expf(x); }
+  static __device__ __forceinline__ float log(float x) { return spec_logf(x); }
+  static __device__ __forceinline__ float pow(float x, float y) { return spec_powf(x, y); }
+};
+
+template <int SOURCE, int ADIABAT, bool P1D>
+static int launch(const CapeArgs& a, cudaStream_t s) {
+  const int threads = 128;
+  const int64_t blocks = (a.ncol + threads - 1) / threads;
+  if (blocks <= 0) return XCAPE_OK;
+  cape_kernel<MathSpec, SOURCE, ADIABAT, P1D><<<(unsigned)blocks, threads, 0, s>>>(a);
+  XC_LAUNCH_CHECK();
+  return XCAPE_OK;
+}
+
+template <int SOURCE, bool P1D>
+static int launch_adiabat(const CapeArgs& a, int adiabat, cudaStream_t s) {
+  switch (adiabat) {
+    case 1: return launch<SOURCE, 1, P1D>(a, s);
+    case 2: return launch<SOURCE, 2, P1D>(a, s);
+    case 3: return launch<SOURCE, 3, P1D>(a, s);
+    case 4: return launch<SOURCE, 4, P1D>(a, s);
+  }
+  return fail(XCAPE_ERR_ARG, "adiabat must be 1..4");
+}
+
+int launch_cape_faithful(const CapeArgs& a, int source, int adiabat, bool p1d, cudaStream_t s) {
+  switch (source) {
+    case 1: return p1d ? launch_adiabat<1, true>(a, adiabat, s) : launch_adiabat<1, false>(a, adiabat, s);
+    case 2: return p1d ? launch_adiabat<2, true>(a, adiabat, s) : launch_adiabat<2, false>(a, adiabat, s);
+    case 3: return p1d ? launch_adiabat<3, true>(a, adiabat, s) : launch_adiabat<3, false>(a, adiabat, s);
+  }
+  return fail(XCAPE_ERR_ARG, "source must be 1..3");
+}
+
+}  // namespace xc

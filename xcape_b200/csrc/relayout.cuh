@@ -1,0 +1,14 @@
+// relayout.cuh — launchers of the glue kernels in relayout.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+namespace xc {
+// level-last [ncol][nlev] (dtype) -> level-major [nlev][ld] float32
+int launch_transpose_cast(const void* in, int dtype, float* out, int64_t ncol, int nlev, int64_t ld, cudaStream_t s);
+// level-last [ncol][nlev] -> level-major [nlev][ld], dtype preserved
+int launch_transpose_same(const void* in, int dtype, void* out, int64_t ncol, int nlev, int64_t ld, cudaStream_t s);
+// flat cast copy (dtype -> float32)
+int launch_cast_copy(const void* in, int dtype, float* out, int64_t n, cudaStream_t s);
+// core.py:286-289
+int launch_pres_lev_pos(const void* p, const void* ps, int dtype, int64_t ncol, int nlev, int32_t* start, cudaStream_t s);
+}  // namespace xc

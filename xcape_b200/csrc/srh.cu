@@ -1,0 +1,34 @@
+// srh.cu — instantiations of the fused SRH kernel and the heights-only kernel.
+// Compiled with -fmad=false so that the binary64 height chain and the binary32 Bunkers
+// chain round operation by operation like the reference.
+#include "xc_common.cuh"
+#include "srh_kernel.cuh"
+#include "srh_launch.cuh"
+
+namespace xc {
+
+template <class T>
+int launch_srh_t(const SrhArgs<T>& a, bool p1d, cudaStream_t s) {
+  if (a.ncol <= 0) return XCAPE_OK;
+  const unsigned blocks = (unsigned)((a.ncol + 127) / 128);
+  if (p1d) srh_kernel<T, true><<<blocks, 128, 0, s>>>(a);
+  else srh_kernel<T, false><<<blocks, 128, 0, s>>>(a);
+  XC_LAUNCH_CHECK();
+  return XCAPE_OK;
+}
+int launch_srh(const SrhArgs<float>& a, bool p1d, cudaStream_t s) { return launch_srh_t(a, p1d, s); }
+int launch_srh(const SrhArgs<double>& a, bool p1d, cudaStream_t s) { return launch_srh_t(a, p1d, s); }
+
+template <class T>
+int launch_height_t(const HeightArgs<T>& a, bool p1d, cudaStream_t s) {
+  if (a.ncol <= 0) return XCAPE_OK;
+  const unsigned blocks = (unsigned)((a.ncol + 127) / 128);
+  if (p1d) stdheight_kernel<T, true><<<blocks, 128, 0, s>>>(a);
+  else stdheight_kernel<T, false><<<blocks, 128, 0, s>>>(a);
+  XC_LAUNCH_CHECK();
+  return XCAPE_OK;
+}
+int launch_stdheight(const HeightArgs<float>& a, bool p1d, cudaStream_t s) { return launch_height_t(a, p1d, s); }
+int launch_stdheight(const HeightArgs<double>& a, bool p1d, cudaStream_t s) { return launch_height_t(a, p1d, s); }
+
+}  // namespace xc

@@ -1,0 +1,268 @@
+// srh_kernel.cuh — fused storm-relative-helicity column kernel (one thread = one column).
+//
+// One upward pass over the column replaces three reference routines and the two full-size
+// float64 height arrays they exchange (core.py:516-535, srh.py:41-61):
+//   stdheight_ml / stdheight_pl   (stdheight_2D_model_lev.f90:74-160)    hypsometric AGL height, binary64
+//   bunkers_calc_ml / _pl         (Bunkers_model_lev.f90:75-180, DINTERP2DZ :188-236)  binary32
+//   DCALRELHL_ml / _pl            (SREH_model_lev.f90:61-129)            binary64
+//
+// Streaming formulation (DESIGN.md §SRH kernel):
+//  * heights are produced level by level and consumed immediately;
+//  * the 12 Bunkers sample heights (500..6000 m) are met in increasing order while heights
+//    increase, so a single cursor replaces DINTERP2DZ's 24 top-down searches;
+//  * the SRH sum  -sum[(u_k-c_u)dv_k - (v_k-c_v)du_k]  needs the storm motion c, which is only
+//    known after the 6 km level; it is accumulated as three c-independent binary64 sums
+//    S1 = sum(u_k dv_k - v_k du_k), S2 = sum dv_k, S3 = sum du_k and combined at the end
+//    (differs from the reference's summation order by O(1e-13) m2/s2);
+//  * levels above max(6 km, depth) are only checked for monotone pressure (loads, no math).
+//    If pressure is not strictly decreasing anywhere (heights not increasing — invalid input
+//    for the reference too) the column is redone by the EXACT path, which reproduces
+//    DINTERP2DZ's "highest bracket wins" search and its orientation switch literally.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace xc {
+
+template <class T>
+struct SrhArgs {
+  const T* __restrict__ p;      // P1D: [nlev]; else level-major [nlev][ld]
+  const T* __restrict__ t;
+  const T* __restrict__ td;
+  const T* __restrict__ u;
+  const T* __restrict__ v;
+  const T* __restrict__ ps;     // [ncol]
+  const T* __restrict__ ts;
+  const T* __restrict__ tds;
+  const T* __restrict__ us;
+  const T* __restrict__ vs;
+  const int32_t* __restrict__ start;   // 1-based or nullptr
+  int64_t ncol, ld;
+  int nlev;
+  double depth, aglh0;
+  double* __restrict__ srh_rm;
+  double* __restrict__ srh_lm;
+  float* __restrict__ rm;       // [2*ncol] or nullptr
+  float* __restrict__ lm;
+  float* __restrict__ mean6;
+};
+
+// stdheight_2D_model_lev.f90:90-125 — binary64 arithmetic on single-precision literals
+// (the SRH goldens pin this detail).
+namespace hc {
+constexpr double R = (double)287.04f, g = (double)-9.80665f, eps = (double)0.6219800858985514f;
+constexpr double t0 = (double)273.15f, c1 = (double)6.112f, c2 = (double)53.49f, c3 = (double)5.09f;
+}  // namespace hc
+
+__device__ __forceinline__ double tvirt(double T, double Td, double P) {
+  const double Tin = T + hc::t0;
+  const double Tdin = Td + hc::t0;
+  const double E = hc::c1 * exp((hc::c2 - (6808 / Tdin) - hc::c3 * log(Tdin)));
+  const double w = hc::eps * (E / (P - E));
+  return Tin * ((w + hc::eps) / (hc::eps * (1 + w)));
+}
+
+__device__ __forceinline__ double interp1(double y1, double y3, double x1, double x2, double x3) {  // SREH_model_lev.f90:123-129
+  if (x3 == x1) x1 = x1 - (double)0.01f;
+  return y1 + ((y3 - y1) * ((x2 - x1) / (x3 - x1)));
+}
+
+struct SrhOut { double srm, slm; float rmu, rmv, lmu, lmv, m6u, m6v; };
+
+__device__ __forceinline__ void bunkers_finish(float mu, float mv, float s1u, float s1v, float s2u, float s2v,
+                                               float s12u, float s12v, float s13u, float s13v, SrhOut& o) {
+  // Bunkers_model_lev.f90:128-177 (accumulators start from 0: SURVEY App. B-8)
+  mu = mu / 13.0f; mv = mv / 13.0f;
+  const float uu = ((0.0f + s12u) + s13u) / 2.0f, vu = ((0.0f + s12v) + s13v) / 2.0f;
+  const float ud = ((0.0f + s1u) + s2u) / 2.0f, vd = ((0.0f + s1v) + s2v) / 2.0f;
+  const float ushr = uu - ud, vshr = vu - vd;
+  const float nrm = sqrtf(ushr * ushr + vshr * vshr);        // (ushr**2+vshr**2)**0.5
+  o.rmu = mu + 7.5f * vshr / nrm;
+  o.rmv = mv - 7.5f * ushr / nrm;
+  o.lmu = mu - 7.5f * vshr / nrm;
+  o.lmv = mv + 7.5f * ushr / nrm;
+  o.m6u = mu; o.m6v = mv;
+}
+
+template <class T, bool P1D>
+__device__ __forceinline__ double ld_p(const SrhArgs<T>& a, int64_t c, int lev) {
+  return (double)(P1D ? __ldg(a.p + lev) : a.p[(int64_t)lev * a.ld + c]);
+}
+
+// Returns false when the column needs the EXACT path (pressure not strictly decreasing).
+template <class T, bool P1D, bool EXACT>
+__device__ bool srh_column(const SrhArgs<T>& a, int64_t c, int ks, SrhOut& o) {
+  const int n3 = a.nlev - ks + 1;                 // 3-D levels used
+  const double Ps = (double)a.ps[c];
+  double Tvp = tvirt((double)a.ts[c], (double)a.tds[c], Ps);
+  double Hp = a.aglh0, Pp = Ps;
+  double up = (double)a.us[c], vp = (double)a.vs[c];
+  float upf = (float)a.us[c], vpf = (float)a.vs[c], zpf = (float)a.aglh0;
+
+  // Bunkers samples: index 0 = surface wind, 1..12 = 500 m .. 6000 m
+  float su[EXACT ? 13 : 1], sv[EXACT ? 13 : 1];
+  float s1u = upf, s1v = vpf, s2u = -999999.0f, s2v = -999999.0f, s12u = -999999.0f, s12v = -999999.0f,
+        s13u = -999999.0f, s13v = -999999.0f;
+  float mu = 0.0f + upf, mv = 0.0f + vpf;         // running in-order sum (fast path)
+  int j = 1;                                      // next sample to find (fast path)
+  if (EXACT) {
+    su[0] = upf; sv[0] = vpf;
+    for (int i = 1; i < 13; ++i) { su[i] = -999999.0f; sv[i] = -999999.0f; }
+  }
+  bool descending = false;
+  if (EXACT) {
+    // DINTERP2DZ orientation test Z(1) > Z(NZ) needs the top height first (f90:211-216)
+    double H = Hp, Tv0 = Tvp, P0 = Pp;
+    for (int i = 0; i < n3; ++i) {
+      const int lev = ks - 1 + i;
+      const int64_t off = (int64_t)lev * a.ld + c;
+      const double P = ld_p<T, P1D>(a, c, lev);
+      const double Tv = tvirt((double)a.t[off], (double)a.td[off], P);
+      H = H + ((hc::R * ((Tv + Tv0) / 2) / hc::g)) * (log(P / P0));
+      Tv0 = Tv; P0 = P;
+    }
+    descending = ((float)a.aglh0 > (float)H);
+  }
+
+  bool found_top = false;
+  double S1 = 0.0, S2 = 0.0, S3 = 0.0;
+  bool mono = true;
+  int i = 0;
+  for (; i < n3; ++i) {
+    const int lev = ks - 1 + i;
+    const int64_t off = (int64_t)lev * a.ld + c;
+    const double P = ld_p<T, P1D>(a, c, lev);
+    if (!(P < Pp)) mono = false;
+    const T uin = a.u[off], vin = a.v[off];
+    const double Tv = tvirt((double)a.t[off], (double)a.td[off], P);
+    // stdheight_2D_model_lev.f90:143,152
+    const double H = Hp + ((hc::R * ((Tv + Tvp) / 2) / hc::g)) * (log(P / Pp));
+    const double uk = (double)uin, vk = (double)vin;
+    const float ukf = (float)uin, vkf = (float)vin, zkf = (float)H;
+
+    // ---- Bunkers samples (DINTERP2DZ, f90:188-236) ----
+    if (EXACT) {
+      const float zlo = descending ? zkf : zpf, zhi = descending ? zpf : zkf;
+      const float vlo_u = descending ? ukf : upf, vhi_u = descending ? upf : ukf;
+      const float vlo_v = descending ? vkf : vpf, vhi_v = descending ? vpf : vkf;
+      for (int s = 1; s < 13; ++s) {               // later (higher) brackets overwrite: == first hit of the top-down search
+        const float h = 500.0f * (float)s;
+        if (zlo <= h && zhi > h) {
+          const float w2 = (h - zlo) / (zhi - zlo);
+          const float w1 = (float)(1.0 - (double)w2);
+          su[s] = w1 * vlo_u + w2 * vhi_u;
+          sv[s] = w1 * vlo_v + w2 * vhi_v;
+        }
+      }
+    } else {
+      while (j < 13) {
+        const float h = 500.0f * (float)j;
+        if (!(zkf > h)) break;                     // sample j is above this layer
+        float qu = -999999.0f, qv = -999999.0f;    // below the layer's base: never bracketed (VMSG)
+        if (zpf <= h) {
+          const float w2 = (h - zpf) / (zkf - zpf);
+          const float w1 = (float)(1.0 - (double)w2);   // 1.D0 - W2 (f90:228)
+          qu = w1 * upf + w2 * ukf;
+          qv = w1 * vpf + w2 * vkf;
+        }
+        mu = mu + qu; mv = mv + qv;
+        if (j == 1) { s2u = qu; s2v = qv; }
+        if (j == 11) { s12u = qu; s12v = qv; }
+        if (j == 12) { s13u = qu; s13v = qv; }
+        ++j;
+      }
+    }
+
+    // ---- SRH partial sums (DCALRELHL, SREH_model_lev.f90:86-114) ----
+    if (!found_top) {
+      double ue = uk, ve = vk;
+      if (H > a.depth) {
+        found_top = true;
+        ue = interp1(uk, up, H, a.depth, Hp);
+        ve = interp1(vk, vp, H, a.depth, Hp);
+      }
+      const double du = ue - up, dv = ve - vp;
+      S1 = S1 + (ue * dv - ve * du);
+      S2 = S2 + dv;
+      S3 = S3 + du;
+    }
+
+    Hp = H; Tvp = Tv; Pp = P; up = uk; vp = vk; upf = ukf; vpf = vkf; zpf = zkf;
+    if (!EXACT && found_top && j >= 13) { ++i; break; }   // nothing above can matter if p keeps decreasing
+  }
+  if (!EXACT) {
+    for (; i < n3; ++i) {                          // monotonicity check only: loads, no math
+      const double P = ld_p<T, P1D>(a, c, ks - 1 + i);
+      if (!(P < Pp)) mono = false;
+      Pp = P;
+    }
+    if (!mono) return false;
+    for (; j < 13; ++j) {                          // column top below the sample height: VMSG enters the mean
+      mu = mu + -999999.0f; mv = mv + -999999.0f;
+      // s2/s12/s13 keep their VMSG initial values
+    }
+  } else {
+    mu = 0.0f; mv = 0.0f;
+    for (int s = 0; s < 13; ++s) { mu = mu + su[s]; mv = mv + sv[s]; }
+    s1u = su[0]; s1v = sv[0]; s2u = su[1]; s2v = sv[1];
+    s12u = su[11]; s12v = sv[11]; s13u = su[12]; s13v = sv[12];
+  }
+  bunkers_finish(mu, mv, s1u, s1v, s2u, s2v, s12u, s12v, s13u, s13v, o);
+  if (found_top) {
+    o.srm = -(S1 - (double)o.rmu * S2 + (double)o.rmv * S3);
+    o.slm = -(S1 - (double)o.lmu * S2 + (double)o.lmv * S3);
+  } else {
+    o.srm = 0.0; o.slm = 0.0;                      // ktop == 0: empty sum (SREH_model_lev.f90:97-103)
+  }
+  return true;
+}
+
+template <class T, bool P1D>
+__global__ void __launch_bounds__(128) srh_kernel(const SrhArgs<T> a) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.ncol) return;
+  int ks = a.start ? a.start[c] : 1;
+  ks = ks < 1 ? 1 : (ks > a.nlev ? a.nlev : ks);
+  SrhOut o;
+  if (!srh_column<T, P1D, false>(a, c, ks, o)) srh_column<T, P1D, true>(a, c, ks, o);
+  a.srh_rm[c] = o.srm; a.srh_lm[c] = o.slm;
+  if (a.rm) { a.rm[2 * c] = o.rmu; a.rm[2 * c + 1] = o.rmv; }
+  if (a.lm) { a.lm[2 * c] = o.lmu; a.lm[2 * c + 1] = o.lmv; }
+  if (a.mean6) { a.mean6[2 * c] = o.m6u; a.mean6[2 * c + 1] = o.m6v; }
+}
+
+// Heights only: loop_stdheight_ml / loop_stdheight_pl1d.  Output strides let the caller pick
+// level-major or level-last.
+template <class T>
+struct HeightArgs {
+  const T* __restrict__ p; const T* __restrict__ t; const T* __restrict__ td;
+  const T* __restrict__ ps; const T* __restrict__ ts; const T* __restrict__ tds;
+  const int32_t* __restrict__ start;
+  int64_t ncol, ld;
+  int nlev;
+  double aglh0;
+  double* __restrict__ h; int64_t h_col_stride, h_lev_stride;
+  double* __restrict__ hs;
+};
+
+template <class T, bool P1D>
+__global__ void __launch_bounds__(128) stdheight_kernel(const HeightArgs<T> a) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.ncol) return;
+  int ks = a.start ? a.start[c] : 1;
+  ks = ks < 1 ? 1 : (ks > a.nlev ? a.nlev : ks);
+  for (int lev = 0; lev < ks - 1; ++lev) a.h[c * a.h_col_stride + lev * a.h_lev_stride] = -999999.0;   // pressure_lev.f90:85-87
+  const double Ps = (double)a.ps[c];
+  double Tvp = tvirt((double)a.ts[c], (double)a.tds[c], Ps), Hp = a.aglh0, Pp = Ps;
+  a.hs[c] = a.aglh0;
+  for (int lev = ks - 1; lev < a.nlev; ++lev) {
+    const int64_t off = (int64_t)lev * a.ld + c;
+    const double P = (double)(P1D ? __ldg(a.p + lev) : a.p[off]);
+    const double Tv = tvirt((double)a.t[off], (double)a.td[off], P);
+    const double H = Hp + ((hc::R * ((Tv + Tvp) / 2) / hc::g)) * (log(P / Pp));
+    a.h[c * a.h_col_stride + lev * a.h_lev_stride] = H;
+    Hp = H; Tvp = Tv; Pp = P;
+  }
+}
+
+}  // namespace xc

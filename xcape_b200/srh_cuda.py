@@ -1,0 +1,100 @@
+"""CUDA counterpart of the reference's ``srh.py`` + ``stdheight.py`` shims.
+
+The reference computes SRH with three f2py calls that exchange two full float64 height
+arrays (core.py:516-535 -> stdheight.py:20-36 -> srh.py:41-61).  ``srh_fused`` makes ONE call
+to ``xcape_cuda_srh`` (include/xcape_b200.h), which produces heights, Bunkers storm motion
+and both helicity integrals in a single pass over the column.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _array as A
+from . import _lib
+from .sharding import column_blocks, run_on_devices
+
+
+def srh_fused(p_2d, t_2d, td_2d, u_2d, v_2d, p_s, t_s, td_s, u_s, v_s, flag_1d, pres_lev_pos, depth,
+              aglh0, type_grid, output, *, device=0, devices=None, stream=None):
+    """
+    Arguments are the union of ``stdheight.stdheight`` (stdheight.py:5) and ``srh.srh``
+    (srh.py:4): ``*_2d`` are ``(nlev, ngrid)``, ``*_s`` are ``(ngrid,)``; ``pres_lev_pos`` may be
+    ``None`` (computed on the device for pressure grids); ``aglh0`` is the scalar height of the
+    surface level (core.py:519 passes 2.0); ``output`` 1 -> ``(srh_rm, srh_lm)``, otherwise
+    ``(srh_rm, srh_lm, rm(2, ngrid), lm(2, ngrid), mean_6km(2, ngrid))`` like srh.py:63-66.
+    srh_* are float64, the storm-motion arrays float32.
+    """
+    L = _lib.lib()
+    nlev, ngrid = t_2d.shape
+    if type_grid == 1:
+        p_is_1d = 0
+    elif type_grid == 2:
+        if flag_1d != 1:
+            raise ValueError('pressure-level grids need a 1-D pressure array (flag_1d == 1)')
+        p_is_1d = 1
+    else:
+        raise ValueError('type_grid must be 1 (model levels) or 2 (pressure levels)')
+    if not np.isscalar(aglh0):
+        raise ValueError('aglh0 must be a scalar height (m)')
+
+    surf = [p_s, t_s, td_s, u_s, v_s]
+    if p_is_1d:
+        f3, f1, p, dt, layout, mem, ref = A.prepare_fields([t_2d, td_2d, u_2d, v_2d], surf, p=p_2d)
+        t_, td_, u_, v_ = f3
+        if p.shape[0] != nlev:
+            raise ValueError('p must have nlev entries')
+    else:
+        f3, f1, _, dt, layout, mem, ref = A.prepare_fields([p_2d, t_2d, td_2d, u_2d, v_2d], surf)
+        p, t_, td_, u_, v_ = f3
+    if any(tuple(a.shape) != (nlev, ngrid) for a in f3) or any(a.shape[0] != ngrid for a in f1):
+        raise ValueError('Input arrays must have the same shape.')
+    ps_, ts_, tds_, us_, vs_ = f1
+
+    start = None
+    if p_is_1d and pres_lev_pos is not None:
+        if A.is_cuda(ref):
+            import torch
+            start = torch.as_tensor(pres_lev_pos, device=ref.device).to(torch.int32).expand(ngrid).contiguous()
+        else:
+            start = np.ascontiguousarray(np.broadcast_to(np.asarray(pres_lev_pos), (ngrid,)), dtype=np.int32)
+
+    want_all = (output != 1)
+    srm = A.empty_like_host_or_device(ref, (ngrid,), 'float64')
+    slm = A.empty_like_host_or_device(ref, (ngrid,), 'float64')
+    # (2, ngrid) in Fortran order == (ngrid, 2) C order
+    rm = A.empty_like_host_or_device(ref, (ngrid, 2), 'float32') if want_all else None
+    lm = A.empty_like_host_or_device(ref, (ngrid, 2), 'float32') if want_all else None
+    m6 = A.empty_like_host_or_device(ref, (ngrid, 2), 'float32') if want_all else None
+    es = 4 if dt == _lib.F32 else 8
+
+    def call(c0, c1, dev):
+        n = c1 - c0
+        if n <= 0:
+            return
+        if not (c0 == 0 and c1 == ngrid) and layout == _lib.LEVEL_MAJOR:
+            raise ValueError('sharding level-major host arrays needs contiguous blocks; pass level-last arrays')
+
+        def off3(a):
+            return A.ptr(a) + (c0 * nlev * es if layout == _lib.LEVEL_LAST else c0 * es)
+
+        def off1(a, e):
+            return None if a is None else A.ptr(a) + c0 * e
+
+        rc = L.xcape_cuda_srh(
+            A.ptr(p) if p_is_1d else off3(p), off3(t_), off3(td_), off3(u_), off3(v_),
+            off1(ps_, es), off1(ts_, es), off1(tds_, es), off1(us_, es), off1(vs_, es),
+            C.c_int64(n), nlev, p_is_1d, dt, layout, mem, C.c_double(float(depth)), C.c_double(float(aglh0)),
+            off1(start, 4), off1(srm, 8), off1(slm, 8), off1(rm, 8), off1(lm, 8), off1(m6, 8),
+            _lib.FAITHFUL, dev, A.stream_of(ref, stream))
+        _lib.check(rc)
+
+    if mem == _lib.MEM_HOST and devices is not None and len(devices) > 1:
+        run_on_devices(lambda b, d: call(b[0], b[1], d), column_blocks(ngrid, len(devices)), list(devices))
+    else:
+        call(0, ngrid, A.device_of(ref, devices[0] if devices else device))
+
+    if not want_all:
+        return srm, slm
+    # hand back the reference's (2, ngrid) view (srh.py:42-43: rm_sup[0, :] is the u component)
+    tr = (lambda a: a.t()) if A.is_cuda(ref) else (lambda a: a.T)
+    return srm, slm, tr(rm), tr(lm), tr(m6)
