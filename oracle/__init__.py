@@ -64,6 +64,8 @@ def vec_math(fn, x, y=None, tmode=SPEC):
     L = lib()
     if fn == 'exp':
         L.xcape_ref_expf_v(_p(x), _p(out), C.c_int64(x.size), C.c_int(tmode))
+    elif fn == 'exp_small':
+        L.xcape_ref_expf_small_v(_p(x), _p(out), C.c_int64(x.size), C.c_int(tmode))
     elif fn == 'log':
         L.xcape_ref_logf_v(_p(x), _p(out), C.c_int64(x.size), C.c_int(tmode))
     else:

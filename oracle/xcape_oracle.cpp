@@ -76,6 +76,20 @@ XC_FMA_TARGET inline double spec_exp_d(double x) {
   return bits2d(d2bits(p) + ((uint64_t)n << 52));
 }
 
+// |x| <= 2^-3: no range reduction, Taylor degree 8 (DESIGN.md "SPEC math": exp_small)
+XC_FMA_TARGET inline double spec_exp_small_d(double x) {
+  double p = 0x1.a01a01a01a01ap-16;                // 1/8!
+  p = __builtin_fma(p, x, 0x1.a01a01a01a01ap-13);  // 1/7!
+  p = __builtin_fma(p, x, 0x1.6c16c16c16c17p-10);  // 1/6!
+  p = __builtin_fma(p, x, 0x1.1111111111111p-7);   // 1/5!
+  p = __builtin_fma(p, x, 0x1.5555555555555p-5);   // 1/4!
+  p = __builtin_fma(p, x, 0x1.5555555555555p-3);   // 1/3!
+  p = __builtin_fma(p, x, 0.5);
+  p = __builtin_fma(p, x, 1.0);
+  p = __builtin_fma(p, x, 1.0);
+  return p;
+}
+
 // natural log of a positive, finite, NORMAL binary64 (every positive finite
 // binary32 converts to one).
 XC_FMA_TARGET inline double spec_log_d(double x) {
@@ -113,6 +127,11 @@ template <int TM> inline float t_exp(float x) {
   if (TM == T_LIBM) return expf(x);
   if (TM == T_CR) return (float)exp((double)x);
   return (float)spec_exp_d((double)x);
+}
+// exp for the theta2 update (f90:460-462), whose argument is almost always tiny
+template <int TM> inline float t_exp_small(float x) {
+  if (TM == T_SPEC && std::fabs(x) <= 0.125f) return (float)spec_exp_small_d((double)x);
+  return t_exp<TM>(x);
 }
 template <int TM> inline float t_log(float x) {
   if (TM == T_LIBM) return logf(x);
@@ -310,8 +329,8 @@ void getcape(const float* pA, const float* tA, const float* tdA, int64_t ls_p, i
         float lhs = c_ls1 - c_ls2 * tbar;
         float rm = c_rd + c_rv * qvbar;
         float cpm = c_cp + c_cpv * qvbar + c_cpl * qlbar + c_cpi * qibar;
-        th2 = th1 * t_exp<TM>(lhv * (ql2 - ql1) / (cpm * tbar) + lhs * (qi2 - qi1) / (cpm * tbar) +
-                              (rm / cpm - c_rddcp) * t_log<TM>(p2 / p1));
+        th2 = th1 * t_exp_small<TM>(lhv * (ql2 - ql1) / (cpm * tbar) + lhs * (qi2 - qi1) / (cpm * tbar) +
+                                    (rm / cpm - c_rddcp) * t_log<TM>(p2 / p1));
         o.n_iter++;
         if (i > 100) {                                           // f90:464-474
           o.cape = 0.0f; o.cin = 0.0f; o.status = ST_NONCONV;
@@ -598,6 +617,8 @@ int xcape_ref_loop_sreh(const double* u, const double* v, const double* z, const
 }
 
 // scalar probes of the transcendental modes (tests compare SPEC vs CR vs LIBM)
+float xcape_ref_expf_small(float x, int tmode) { return tmode == 0 ? t_exp_small<0>(x) : tmode == 1 ? t_exp_small<1>(x) : t_exp_small<2>(x); }
+void xcape_ref_expf_small_v(const float* x, float* y, int64_t n, int tmode) { for (int64_t i = 0; i < n; ++i) y[i] = xcape_ref_expf_small(x[i], tmode); }
 float xcape_ref_expf(float x, int tmode) { return tmode == 0 ? t_exp<0>(x) : tmode == 1 ? t_exp<1>(x) : t_exp<2>(x); }
 float xcape_ref_logf(float x, int tmode) { return tmode == 0 ? t_log<0>(x) : tmode == 1 ? t_log<1>(x) : t_log<2>(x); }
 float xcape_ref_powf(float x, float y, int tmode) { return tmode == 0 ? t_pow<0>(x, y) : tmode == 1 ? t_pow<1>(x, y) : t_pow<2>(x, y); }

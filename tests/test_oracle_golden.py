@@ -78,6 +78,8 @@ def test_spec_math_is_a_valid_libm(oracle_mod):
     assert (oracle_mod.vec_math('exp', x, tmode=2) != oracle_mod.vec_math('exp', x, tmode=1)).mean() < 1e-4
     x = rng.uniform(-0.05, 0.05, 500_000).astype(np.float32)
     assert (oracle_mod.vec_math('exp', x, tmode=2) != oracle_mod.vec_math('exp', x, tmode=1)).mean() < 1e-4
+    x = rng.uniform(-0.2, 0.2, 500_000).astype(np.float32)     # straddles the 2^-3 switch of exp_small
+    assert (oracle_mod.vec_math('exp_small', x, tmode=2) != oracle_mod.vec_math('exp', x, tmode=1)).mean() < 1e-4
     x = np.exp(rng.uniform(-8, 8, 500_000)).astype(np.float32)
     assert (oracle_mod.vec_math('log', x, tmode=2) != oracle_mod.vec_math('log', x, tmode=1)).mean() < 1e-4
     x = rng.uniform(0.0005, 1.1, 500_000).astype(np.float32)

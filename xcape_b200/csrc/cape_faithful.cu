@@ -10,6 +10,7 @@ namespace xc {
 
 struct MathSpec {
   static __device__ __forceinline__ float exp(float x) { return spec_expf(x); }
+  static __device__ __forceinline__ float exp_small(float x) { return spec_expf_small(x); }
   static __device__ __forceinline__ float log(float x) { return spec_logf(x); }
   static __device__ __forceinline__ float pow(float x, float y) { return spec_powf(x, y); }
 };

@@ -1,7 +1,7 @@
 // relayout.cu — HBM-bound glue kernels in front of the column kernels:
 //   * transpose_cast: level-last [ncol][nlev] (the reference's f2py layout, core.py:44-50)
 //     -> level-major [nlev][ld] binary32, fused with the f2py float64->float32 down-cast
-//     (SURVEY §8b "Ownership"); 32x32 shared-memory tiles, both sides coalesced;
+//     (SURVEY §8b "Ownership"); column-block shared-memory staging, both sides coalesced;
 //   * cast_copy: dtype cast of already level-major / 1-D arrays;
 //   * pres_lev_pos: core.py:286-289 (numpy masked argmin) evaluated in the input dtype.
 #include "xc_common.cuh"
@@ -9,24 +9,30 @@
 
 namespace xc {
 
+// Column-block transpose.  A CTA owns TC consecutive columns: in the level-last input they are
+// ONE contiguous run of TC*nlev elements, read with fully coalesced loads whatever nlev is
+// (37, 50, 137 ...); the run is parked in shared memory with an odd row stride (no bank
+// conflicts on the transposed read) and written out as nlev rows of TC consecutive columns.
+constexpr int kTC = 64;
 template <class T, class TO>
 __global__ void __launch_bounds__(256) transpose_cast_kernel(const T* __restrict__ in, TO* __restrict__ out,
                                                              int64_t ncol, int nlev, int64_t ld) {
-  __shared__ TO tile[32][33];
-  const int64_t c0 = (int64_t)blockIdx.x * 32;
-  const int l0 = blockIdx.y * 32;
-  // read: threadIdx.x walks levels (contiguous in the level-last input)
-  for (int j = threadIdx.y; j < 32; j += 8) {
-    const int64_t c = c0 + j;
-    const int l = l0 + threadIdx.x;
-    if (c < ncol && l < nlev) tile[j][threadIdx.x] = (TO)in[c * nlev + l];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TO* tile = reinterpret_cast<TO*>(smem_raw);
+  const int S = nlev | 1;                                  // odd stride
+  const int64_t c0 = (int64_t)blockIdx.x * kTC;
+  const int nc = (int)min((int64_t)kTC, ncol - c0);
+  const int nelem = nc * nlev;
+  const T* src = in + c0 * nlev;
+  for (int i = threadIdx.x; i < nelem; i += blockDim.x) {
+    const int c = i / nlev, l = i - c * nlev;
+    tile[c * S + l] = (TO)src[i];
   }
   __syncthreads();
-  // write: threadIdx.x walks columns (contiguous in the level-major output)
-  for (int j = threadIdx.y; j < 32; j += 8) {
-    const int l = l0 + j;
-    const int64_t c = c0 + threadIdx.x;
-    if (c < ncol && l < nlev) out[(int64_t)l * ld + c] = tile[threadIdx.x][j];
+  // write: consecutive threads -> consecutive columns of one level row
+  for (int i = threadIdx.x; i < nlev * kTC; i += blockDim.x) {
+    const int l = i / kTC, c = i - l * kTC;
+    if (c < nc) out[(int64_t)l * ld + c0 + c] = tile[c * S + l];
   }
 }
 
@@ -63,20 +69,32 @@ static inline unsigned grid_for(int64_t n, int threads, int64_t cap = 148 * 32) 
 
 int launch_transpose_cast(const void* in, int dtype, float* out, int64_t ncol, int nlev, int64_t ld, cudaStream_t s) {
   if (ncol <= 0) return XCAPE_OK;
-  dim3 block(32, 8);
-  dim3 grid((unsigned)((ncol + 31) / 32), (unsigned)((nlev + 31) / 32));
-  if (dtype == XCAPE_F64) transpose_cast_kernel<double, float><<<grid, block, 0, s>>>((const double*)in, out, ncol, nlev, ld);
-  else transpose_cast_kernel<float, float><<<grid, block, 0, s>>>((const float*)in, out, ncol, nlev, ld);
+  const unsigned grid = (unsigned)((ncol + kTC - 1) / kTC);
+  const size_t smem = (size_t)kTC * (nlev | 1) * sizeof(float);
+  if (smem > 200 * 1024) return fail(XCAPE_ERR_ARG, "nlev too large for the relayout kernel (max ~790 levels)");
+  if (dtype == XCAPE_F64) {
+    XC_CUDA(cudaFuncSetAttribute(transpose_cast_kernel<double, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    transpose_cast_kernel<double, float><<<grid, 256, smem, s>>>((const double*)in, out, ncol, nlev, ld);
+  } else {
+    XC_CUDA(cudaFuncSetAttribute(transpose_cast_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    transpose_cast_kernel<float, float><<<grid, 256, smem, s>>>((const float*)in, out, ncol, nlev, ld);
+  }
   XC_LAUNCH_CHECK();
   return XCAPE_OK;
 }
 
 int launch_transpose_same(const void* in, int dtype, void* out, int64_t ncol, int nlev, int64_t ld, cudaStream_t s) {
   if (ncol <= 0) return XCAPE_OK;
-  dim3 block(32, 8);
-  dim3 grid((unsigned)((ncol + 31) / 32), (unsigned)((nlev + 31) / 32));
-  if (dtype == XCAPE_F64) transpose_cast_kernel<double, double><<<grid, block, 0, s>>>((const double*)in, (double*)out, ncol, nlev, ld);
-  else transpose_cast_kernel<float, float><<<grid, block, 0, s>>>((const float*)in, (float*)out, ncol, nlev, ld);
+  const unsigned grid = (unsigned)((ncol + kTC - 1) / kTC);
+  const size_t smem = (size_t)kTC * (nlev | 1) * esize(dtype);
+  if (smem > 200 * 1024) return fail(XCAPE_ERR_ARG, "nlev too large for the relayout kernel");
+  if (dtype == XCAPE_F64) {
+    XC_CUDA(cudaFuncSetAttribute(transpose_cast_kernel<double, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    transpose_cast_kernel<double, double><<<grid, 256, smem, s>>>((const double*)in, (double*)out, ncol, nlev, ld);
+  } else {
+    XC_CUDA(cudaFuncSetAttribute(transpose_cast_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    transpose_cast_kernel<float, float><<<grid, 256, smem, s>>>((const float*)in, (float*)out, ncol, nlev, ld);
+  }
   XC_LAUNCH_CHECK();
   return XCAPE_OK;
 }
