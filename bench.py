@@ -207,13 +207,22 @@ def main():
     g = {k: torch.from_numpy(d[k]).to(dev) for k in ('p', 't', 'td', 'ps', 'ts', 'tds')}
     sampler = ClockSampler(local_rank)
     if rank == 0:
+        # nvidia-smi's start-up (NVML init) stalls the GPU for tens of ms: let it reach its steady
+        # sampling state before anything is timed
         sampler.start()
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 5.0:
+            time.sleep(0.05)
     windows = []
 
     def step_dev():
         return run_cape(g['p'], g['t'].t(), g['td'].t(), g['ps'], g['ts'], g['tds'])
 
     for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    t_warm = time.time()
+    while time.time() - t_warm < 0.5:      # clocks / power state settled (untimed)
         step_dev()
     barrier()
     l0 = _lib.kernel_launches()
