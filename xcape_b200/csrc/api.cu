@@ -226,8 +226,17 @@ int height_device_t(const void* p, const void* t, const void* td, const void* ps
 // outputs come D2H — all stream-ordered, so blocks on different streams overlap copy and
 // compute.  Pageable host memory works (the driver stages it); pinned memory overlaps fully.
 // ---------------------------------------------------------------------------------------
-constexpr int kStreams = 3;
-constexpr int64_t kChunkCols = 1 << 18;
+constexpr int kMaxStreams = 8;
+inline int64_t env_i64(const char* name, int64_t dflt, int64_t lo, int64_t hi) {
+  if (const char* e = getenv(name)) {
+    const long long v = atoll(e);
+    if (v >= lo && v <= hi) return v;
+  }
+  return dflt;
+}
+// Tunables of the host-pointer path (columns per staged block, streams in the ring).
+inline int64_t chunk_cols() { return env_i64("XCAPE_B200_CHUNK_COLS", 1 << 17, 1024, 1 << 26); }
+inline int ring_streams() { return (int)env_i64("XCAPE_B200_STREAMS", 4, 1, kMaxStreams); }
 
 struct HostIn3 { const void* host; };                    // [ncol][nlev] or [nlev][ncol], es bytes/element
 struct HostIn1 { const void* host; size_t es; };          // [ncol]
@@ -256,10 +265,10 @@ cudaError_t d2h_field(void* dst, const void* src, int layout, int64_t ncol, int 
 template <class F>
 int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_host, const std::vector<HostIn3>& in3,
                const std::vector<HostIn1>& in1, const std::vector<HostOut>& outs, F launch) {
-  const int64_t chunk = std::min<int64_t>(ncol, kChunkCols);
-  const int nstream = (int)std::min<int64_t>(kStreams, (ncol + chunk - 1) / chunk);
-  cudaStream_t st[kStreams] = {};
-  Block b[kStreams];
+  const int64_t chunk = std::min<int64_t>(ncol, chunk_cols());
+  const int nstream = (int)std::min<int64_t>(ring_streams(), (ncol + chunk - 1) / chunk);
+  cudaStream_t st[kMaxStreams] = {};
+  Block b[kMaxStreams];
   auto body = [&]() -> int {
     for (int i = 0; i < nstream; ++i) {
       XC_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
