@@ -262,21 +262,77 @@ cudaError_t d2h_field(void* dst, const void* src, int layout, int64_t ncol, int 
                            cudaMemcpyDeviceToHost, s);
 }
 
+// Pinned host staging buffers, cached process-wide (cudaHostAlloc costs milliseconds).
+struct PinnedCache {
+  struct Ent { void* p; size_t bytes; bool used; };
+  std::mutex mu;
+  std::vector<Ent> ents;
+  void* acquire(size_t bytes) {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& e : ents)
+      if (!e.used && e.bytes >= bytes) { e.used = true; return e.p; }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ents.push_back({p, bytes, true});
+    return p;
+  }
+  void release(void* p) {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& e : ents)
+      if (e.p == p) e.used = false;
+  }
+};
+PinnedCache g_pinned;
+
+bool is_pageable_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+// A D2H copy into PAGEABLE memory blocks the host until the producing kernel has finished, which
+// would serialise the ring (r1c probe: one block per field was faster than four).  Per-column
+// outputs are therefore landed in a pinned staging slot per stream and copied to the caller's
+// arrays by the host once the slot's event fires — while later blocks are still running.
 template <class F>
 int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_host, const std::vector<HostIn3>& in3,
                const std::vector<HostIn1>& in1, const std::vector<HostOut>& outs, F launch) {
   const int64_t chunk = std::min<int64_t>(ncol, chunk_cols());
   const int nstream = (int)std::min<int64_t>(ring_streams(), (ncol + chunk - 1) / chunk);
   cudaStream_t st[kMaxStreams] = {};
+  cudaEvent_t done[kMaxStreams] = {};
   Block b[kMaxStreams];
+  struct Pending { bool on = false; int64_t c0 = 0, n = 0; } pend[kMaxStreams];
+  std::vector<void*> stage[kMaxStreams];          // pinned staging per output (nullptr = direct copy)
+  std::vector<char> staged(outs.size(), 0);
+  for (size_t k = 0; k < outs.size(); ++k)
+    staged[k] = (outs[k].host && !outs[k].is3d && is_pageable_host(outs[k].host)) ? 1 : 0;
+
+  auto drain = [&](int i) -> int {                // wait for slot i's block, hand its outputs to the caller
+    if (!pend[i].on) return XCAPE_OK;
+    XC_CUDA(cudaEventSynchronize(done[i]));
+    for (size_t k = 0; k < outs.size(); ++k)
+      if (staged[k])
+        memcpy((char*)outs[k].host + (size_t)pend[i].c0 * outs[k].bytes_per_col, stage[i][k], (size_t)pend[i].n * outs[k].bytes_per_col);
+    pend[i].on = false;
+    return XCAPE_OK;
+  };
+
   auto body = [&]() -> int {
     for (int i = 0; i < nstream; ++i) {
       XC_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+      XC_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
       for (size_t k = 0; k < in3.size(); ++k) { void* q; XC_CUDA(pool_alloc(&q, (size_t)chunk * nlev * es, st[i])); b[i].in3.push_back(q); }
       for (size_t k = 0; k < in1.size(); ++k) { void* q; XC_CUDA(pool_alloc(&q, (size_t)chunk * in1[k].es, st[i])); b[i].in1.push_back(q); }
       for (size_t k = 0; k < outs.size(); ++k) {
         void* q; XC_CUDA(pool_alloc(&q, (size_t)chunk * (outs[k].is3d ? (size_t)nlev * 8 : outs[k].bytes_per_col), st[i]));
         b[i].out.push_back(q);
+        void* h = nullptr;
+        if (staged[k]) {
+          h = g_pinned.acquire((size_t)chunk * outs[k].bytes_per_col);
+          if (!h) return fail(XCAPE_ERR_CUDA, "cudaHostAlloc failed for the output staging buffer");
+        }
+        stage[i].push_back(h);
       }
       if (p1d_host) {
         XC_CUDA(pool_alloc(&b[i].p1d, (size_t)nlev * es, st[i]));
@@ -287,16 +343,24 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
     for (int64_t c0 = 0; c0 < ncol; c0 += chunk, i = (i + 1) % nstream) {
       const int64_t n = std::min<int64_t>(chunk, ncol - c0);
       cudaStream_t s = st[i];
+      int r = drain(i);                            // slot reuse: its previous block must have left
+      if (r) return r;
       for (size_t k = 0; k < in3.size(); ++k) XC_CUDA(h2d_field(b[i].in3[k], in3[k].host, layout, ncol, nlev, c0, n, es, s));
       for (size_t k = 0; k < in1.size(); ++k)
         XC_CUDA(cudaMemcpyAsync(b[i].in1[k], (const char*)in1[k].host + (size_t)c0 * in1[k].es, (size_t)n * in1[k].es, cudaMemcpyHostToDevice, s));
-      int r = launch(b[i], n, s);
-      if (r) return r;
+      if ((r = launch(b[i], n, s))) return r;
       for (size_t k = 0; k < outs.size(); ++k) {
         if (!outs[k].host) continue;
         if (outs[k].is3d) XC_CUDA(d2h_field(outs[k].host, b[i].out[k], layout, ncol, nlev, c0, n, 8, s));
+        else if (staged[k]) XC_CUDA(cudaMemcpyAsync(stage[i][k], b[i].out[k], (size_t)n * outs[k].bytes_per_col, cudaMemcpyDeviceToHost, s));
         else XC_CUDA(cudaMemcpyAsync((char*)outs[k].host + (size_t)c0 * outs[k].bytes_per_col, b[i].out[k], (size_t)n * outs[k].bytes_per_col, cudaMemcpyDeviceToHost, s));
       }
+      XC_CUDA(cudaEventRecord(done[i], s));
+      pend[i].on = true; pend[i].c0 = c0; pend[i].n = n;
+    }
+    for (int k = 0; k < nstream; ++k) {            // oldest block first
+      int r = drain((i + k) % nstream);
+      if (r) return r;
     }
     for (int k = 0; k < nstream; ++k) XC_CUDA(cudaStreamSynchronize(st[k]));
     return XCAPE_OK;
@@ -304,13 +368,16 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
   int rc = body();
   std::string keep = g_last_error;
   for (int i = 0; i < nstream; ++i) {
-    if (!st[i]) continue;
-    for (void* q : b[i].in3) cudaFreeAsync(q, st[i]);
-    for (void* q : b[i].in1) cudaFreeAsync(q, st[i]);
-    for (void* q : b[i].out) cudaFreeAsync(q, st[i]);
-    if (b[i].p1d) cudaFreeAsync(b[i].p1d, st[i]);
-    cudaStreamSynchronize(st[i]);
-    cudaStreamDestroy(st[i]);
+    if (st[i]) {
+      for (void* q : b[i].in3) cudaFreeAsync(q, st[i]);
+      for (void* q : b[i].in1) cudaFreeAsync(q, st[i]);
+      for (void* q : b[i].out) cudaFreeAsync(q, st[i]);
+      if (b[i].p1d) cudaFreeAsync(b[i].p1d, st[i]);
+      cudaStreamSynchronize(st[i]);
+      cudaStreamDestroy(st[i]);
+    }
+    if (done[i]) cudaEventDestroy(done[i]);
+    for (void* h : stage[i]) if (h) g_pinned.release(h);
   }
   if (rc) { cudaGetLastError(); g_last_error = keep; }
   return rc;
