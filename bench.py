@@ -1,27 +1,32 @@
 #!/usr/bin/env python
-"""bench.py — CAPE/CIN columns/sec on the ERA5-shape most-unstable workload (BASELINE.json).
+"""bench.py — columns/sec of the xcape column hot path on B200 (headline: BASELINE.json's metric).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on host cores
+    python bench.py --workload {C2,C3,C4,C5} ...             # C2 (default) is the headline
     (N > 1: launched by torchrun, one rank per GPU)
 
-One "step" = one pass of the hot path (calc_cape, most-unstable parcel, pinc = 500 Pa,
-pseudo-liquid adiabat) over one synthetic ERA5 pressure-level field: 721 x 1440 columns x 37
-levels (BASELINE configs[1], "C2").  Weak scaling: every rank owns one such field (a different
-time step of the stack — SURVEY §8e shards time chunks / column blocks, no collective).
+One "step" = one pass of the hot path over one synthetic field.  The default workload is
+BASELINE configs[1] ("C2"): calc_cape, most-unstable parcel, pinc = 500 Pa, pseudo-liquid adiabat,
+ERA5 pressure levels, 721 x 1440 columns x 37 levels.  Other workloads (same JSON contract):
+C3 = calc_cape mixed-layer 500 m on HRRR-shape 1059 x 1799 x 50 model levels, C4 = calc_srh 0-3 km
+on the same grid, C5 = calc_cape most-unstable on ONE time step (721 x 1440) of the 137-level
+stack per rank.  Weak scaling: every rank owns one field (a time step of the stack; SURVEY §8e
+shards time chunks / column blocks, no collective).
 
 Numbers on the JSON line:
   value      whole-job columns/s with the field resident in HBM in the reference's own layout
              ([ncol, nlev] float32, level last); the timed call is the public device-pointer
-             path: pres_lev_pos + relayout + CAPE kernel, CUDA events on the launch stream.
+             path (pres_lev_pos + relayout + kernel), CUDA events on the launch stream.
   e2e        same metric through the host-buffer C-ABI call (pinned host numpy in, host numpy
              out, H2D / D2H inside the timed region).
-  roofline   the CAPE kernel alone (level-major input, one launch per step, CUDA events):
-             algorithmic work = 73 flop x (moist iterations executed, counted by the kernel
-             and asserted equal to the oracle's count in tests) against the FFMA peak measured
-             on this GPU by xcape_cuda_measure_peaks; plus the HBM view (324 B/column).
-  cpu_baseline  the CPU oracle in LIBM mode (= the reference algorithm with the libm gfortran
-             links) on all host threads over a bounded sample of the same field (rank 0, N=1).
+  roofline   the dominant kernel alone (level-major input, exactly one launch per step, CUDA
+             events).  CAPE: FP-issue bound — algorithmic work = 73 flop x (moist iterations
+             executed, counted by the kernel; tests assert the count equals the oracle's) against
+             the FFMA peak measured on this GPU by xcape_cuda_measure_peaks, plus the HBM view.
+             SRH: HBM bound — 1028 B/column against MEASURED_PEAKS.json's copy bandwidth.
+  cpu_baseline  the CPU oracle (= the reference algorithm; CAPE with the libm gfortran links) on
+             all host threads over a bounded sample of the same field (rank 0, N = 1).
 """
 import argparse
 import json
@@ -37,11 +42,8 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-METRIC = 'CAPE/CIN columns/sec (ERA5-shape, MU parcel)'
 UNIT = 'columns/s'
-WORKLOAD = 'calc_cape most-unstable, ERA5 pressure levels 721x1440x37, pinc=500 Pa, pseudo-liquid (configs[1])'
 FLOP_PER_ITER = 73.0
-BYTES_PER_COL = 324.0         # 4*(2*37) + 12 + 16
 
 
 class ClockSampler:
@@ -101,49 +103,215 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def cpu_reference_rate(d, ncol_sample, nthreads, counters=False):
-    """Reference algorithm (oracle, LIBM arithmetic) on `ncol_sample` columns spread evenly over
-    the field; returns (columns/s, mean iterations/column or None)."""
-    import oracle
-    ncol = d['t'].shape[0]
-    stride = max(1, ncol // ncol_sample)
-    idx = np.arange(0, ncol, stride)[:ncol_sample]
-    sub = [np.ascontiguousarray(d[k][idx]) for k in ('t', 'td', 'ps', 'ts', 'tds')]
-    t0 = time.perf_counter()
-    out = oracle.calc_cape_ref(d['p'], *sub, source='most-unstable', pinc=500., adiabat='pseudo-liquid',
-                               vertical_lev='pressure', tmode=oracle.LIBM, nthreads=nthreads, counters=counters)
-    dt = time.perf_counter() - t0
-    it = float(out[1]['n_iter'].mean()) if counters else None
-    return len(idx) / dt, it, len(idx)
+class CapeWorkload:
+    """calc_cape on a named synthetic configuration."""
+    kind = 'cape'
+
+    def __init__(self, cfg, source, ml_depth, metric, workload):
+        self.cfg, self.source, self.ml_depth = cfg, source, float(ml_depth)
+        self.src_id = {'surface': 1, 'most-unstable': 2, 'mixed-layer': 3}[source]
+        self.metric, self.workload = metric, workload
+        self.fields3 = ('t', 'td')
+
+    def make(self, rank, cols):
+        from xcape_b200.synthetic import CONFIGS, make_soundings
+        kw = {}
+        if self.cfg == 'C5':                   # one time step (721 x 1440) of the 24-step stack per rank
+            kw['grid'] = (721, 1440)
+        d = make_soundings(self.cfg, seed=CONFIGS[self.cfg]['seed'] + rank, cols=(0, cols) if cols else None,
+                           winds=False, **kw)
+        self.p1d = d['p'].ndim == 1
+        self.ncol, self.nlev = d['t'].shape
+        if not self.p1d:
+            self.fields3 = ('p', 't', 'td')
+        self.bytes_per_col = 4.0 * (len(self.fields3) * self.nlev) + 12 + (16 if self.src_id == 2 else 8)
+        return d
+
+    def _call(self, p, t2, td2, ps, ts, tds, plp, **kw):
+        from xcape_b200.cape_cuda import cape
+        return cape(p, t2, td2, ps, ts, tds, 1 if self.p1d else 0, plp, self.src_id, self.ml_depth, 1, 500.,
+                    2 if self.p1d else 1, **kw)
+
+    def to_device(self, d, dev):
+        import torch
+        return {k: torch.from_numpy(d[k]).to(dev) for k in ('p', 't', 'td', 'ps', 'ts', 'tds')}
+
+    def step_dev(self, g):
+        p = g['p'] if self.p1d else g['p'].t()
+        return self._call(p, g['t'].t(), g['td'].t(), g['ps'], g['ts'], g['tds'], None)
+
+    def kernel_state(self, g):
+        from xcape_b200.cape_cuda import pres_lev_pos
+        st = dict(t=g['t'].t().contiguous(), td=g['td'].t().contiguous(),
+                  p=g['p'] if self.p1d else g['p'].t().contiguous(),
+                  plp=pres_lev_pos(g['p'], g['ps']) if self.p1d else 1)
+        cnt = self._call(st['p'], st['t'], st['td'], g['ps'], g['ts'], g['tds'], st['plp'], return_counters=True)
+        st['total_iter'] = float(cnt[5].double().sum().item())
+        return st
+
+    def step_kernel(self, g, st):
+        return self._call(st['p'], st['t'], st['td'], g['ps'], g['ts'], g['tds'], st['plp'])
+
+    def pinned(self, d):
+        import torch
+        keys = self.fields3 + ('ps', 'ts', 'tds')
+        pin = {k: torch.empty(d[k].shape, dtype=torch.float32).pin_memory() for k in keys}
+        for k in keys:
+            pin[k].numpy()[...] = d[k]
+        hp = {k: v.numpy() for k, v in pin.items()}
+        hp['_keep'] = pin
+        if self.p1d:
+            hp['p'] = d['p']
+        return hp
+
+    def step_e2e(self, hp, device):
+        p = hp['p'] if self.p1d else hp['p'].T
+        return self._call(p, hp['t'].T, hp['td'].T, hp['ps'], hp['ts'], hp['tds'], None, device=device)
+
+    def io_bytes(self):
+        h2d = int(len(self.fields3) * self.ncol * self.nlev * 4 + 3 * self.ncol * 4 + (self.nlev * 4 if self.p1d else 0))
+        return h2d, int(16 * self.ncol)
+
+    def cpu_rate(self, d, nsample, nthreads, counters=False):
+        import oracle
+        idx = np.arange(0, self.ncol, max(1, self.ncol // nsample))[:nsample]
+        sub = {k: np.ascontiguousarray(d[k][idx]) for k in ('t', 'td', 'ps', 'ts', 'tds')}
+        p = d['p'] if self.p1d else np.ascontiguousarray(d['p'][idx])
+        t0 = time.perf_counter()
+        out = oracle.calc_cape_ref(p, sub['t'], sub['td'], sub['ps'], sub['ts'], sub['tds'], source=self.source,
+                                   ml_depth=self.ml_depth, pinc=500., adiabat='pseudo-liquid',
+                                   vertical_lev='pressure' if self.p1d else 'sigma', tmode=oracle.LIBM,
+                                   nthreads=nthreads, counters=counters)
+        dt = time.perf_counter() - t0
+        note = f"; {float(out[1]['n_iter'].mean()):.1f} iterations/column" if counters else ''
+        return len(idx) / dt, len(idx), 'oracle tmode=LIBM (reference algorithm, glibc libm)' + note
+
+    def roofline(self, ms_kernel, st, fp32_peak, fp64_peak, hbm_peak, hbm_src):
+        tf = FLOP_PER_ITER * st['total_iter'] / (ms_kernel * 1e-3) / 1e12
+        gbs = self.bytes_per_col * self.ncol / (ms_kernel * 1e-3) / 1e9
+        return {
+            'bound': 'fp32', 'achieved': tf, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': tf / fp32_peak, 'traffic': None,
+            'kernel': f'cape_kernel<MathSpec,{self.src_id},1,{str(self.p1d).lower()}>', 'kernel_ms': ms_kernel,
+            'work': f"{FLOP_PER_ITER:.0f} flop x {st['total_iter'] / self.ncol:.1f} moist iterations/column (counted by the kernel)",
+            'peak_source': 'FFMA microbenchmark on this GPU (xcape_cuda_measure_peaks), 2 flop/FMA',
+            'fp64_peak_tflops': fp64_peak, 'iterations_per_s': st['total_iter'] / (ms_kernel * 1e-3),
+            'hbm': {'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
+                    'bytes_per_column': self.bytes_per_col, 'peak_source': hbm_src}}
 
 
-def run_reference(args, rank, world):
+class SrhWorkload:
+    """calc_srh (0-3 km, Bunkers storm motion) on a named synthetic configuration."""
+    kind = 'srh'
+    KEYS3 = ('p', 't', 'td', 'u', 'v')
+    KEYS1 = ('ps', 'ts', 'tds', 'us', 'vs')
+
+    def __init__(self, cfg, metric, workload):
+        self.cfg, self.metric, self.workload = cfg, metric, workload
+
+    def make(self, rank, cols):
+        from xcape_b200.synthetic import CONFIGS, make_soundings
+        d = make_soundings(self.cfg, seed=CONFIGS[self.cfg]['seed'] + rank, cols=(0, cols) if cols else None)
+        self.ncol, self.nlev = d['t'].shape
+        self.bytes_per_col = 4.0 * (5 * self.nlev) + 20 + 8          # SURVEY §8d
+        return d
+
+    def _call(self, a, output=1, **kw):
+        from xcape_b200.srh_cuda import srh_fused
+        return srh_fused(a['p'], a['t'], a['td'], a['u'], a['v'], a['ps'], a['ts'], a['tds'], a['us'], a['vs'],
+                         0, None, 3000, 2., 1, output, **kw)
+
+    def to_device(self, d, dev):
+        import torch
+        return {k: torch.from_numpy(d[k]).to(dev) for k in self.KEYS3 + self.KEYS1}
+
+    def step_dev(self, g):
+        a = {k: g[k].t() for k in self.KEYS3}
+        a.update({k: g[k] for k in self.KEYS1})
+        return self._call(a)
+
+    def kernel_state(self, g):
+        st = {k: g[k].t().contiguous() for k in self.KEYS3}
+        st.update({k: g[k] for k in self.KEYS1})
+        return st
+
+    def step_kernel(self, g, st):
+        return self._call(st)
+
+    def pinned(self, d):
+        import torch
+        pin = {k: torch.empty(d[k].shape, dtype=torch.float32).pin_memory() for k in self.KEYS3 + self.KEYS1}
+        for k in pin:
+            pin[k].numpy()[...] = d[k]
+        hp = {k: v.numpy() for k, v in pin.items()}
+        hp['_keep'] = pin
+        return hp
+
+    def step_e2e(self, hp, device):
+        a = {k: hp[k].T for k in self.KEYS3}
+        a.update({k: hp[k] for k in self.KEYS1})
+        return self._call(a, device=device)
+
+    def io_bytes(self):
+        return int(5 * self.ncol * self.nlev * 4 + 5 * self.ncol * 4), int(16 * self.ncol)
+
+    def cpu_rate(self, d, nsample, nthreads, counters=False):
+        import oracle
+        idx = np.arange(0, self.ncol, max(1, self.ncol // nsample))[:nsample]
+        sub = [np.ascontiguousarray(d[k][idx]) for k in self.KEYS3 + self.KEYS1]
+        t0 = time.perf_counter()
+        oracle.calc_srh_ref(*sub, depth=3000, vertical_lev='sigma', output_var='srh', nthreads=nthreads)
+        dt = time.perf_counter() - t0
+        return len(idx) / dt, len(idx), 'oracle stdheight+Bunkers+SREH chain (reference algorithm)'
+
+    def roofline(self, ms_kernel, st, fp32_peak, fp64_peak, hbm_peak, hbm_src):
+        gbs = self.bytes_per_col * self.ncol / (ms_kernel * 1e-3) / 1e9
+        return {'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak, 'traffic': None,
+                'kernel': 'srh_kernel<float,false>', 'kernel_ms': ms_kernel, 'bytes_per_column': self.bytes_per_col,
+                'peak_source': hbm_src, 'fp64_peak_tflops': fp64_peak,
+                'note': 'faithful mode evaluates the hypsometric exp/log chain in binary64 (reference arithmetic)'}
+
+
+def get_workload(name):
+    if name == 'C2':
+        return CapeWorkload('C2', 'most-unstable', 500., 'CAPE/CIN columns/sec (ERA5-shape, MU parcel)',
+                            'calc_cape most-unstable, ERA5 pressure levels 721x1440x37, pinc=500 Pa, pseudo-liquid (configs[1])')
+    if name == 'C3':
+        return CapeWorkload('C3', 'mixed-layer', 500., 'CAPE/CIN columns/sec (HRRR-shape, ML parcel)',
+                            'calc_cape mixed-layer (ml_depth=500 m), HRRR model levels 1059x1799x50, pinc=500 Pa (configs[2])')
+    if name == 'C4':
+        return SrhWorkload('C4', 'SRH columns/sec (HRRR-shape, 0-3 km, Bunkers)',
+                           'calc_srh 0-3 km with Bunkers storm motion, HRRR model levels 1059x1799x50 (configs[3])')
+    if name == 'C5':
+        return CapeWorkload('C5', 'most-unstable', 500., 'CAPE/CIN columns/sec (ERA5 137 model levels, MU parcel)',
+                            'calc_cape most-unstable, one 721x1440x137 time step of the 24-step stack per GPU (configs[4])')
+    raise SystemExit(f'unknown workload {name}')
+
+
+def run_reference(args, rank, world, wl):
     """--impl reference: the reference's CPU algorithm on this box's host cores."""
     if rank != 0:
         return
     import oracle
-    from xcape_b200.synthetic import make_soundings
     oracle.build()
     nth = host_threads()
-    d = make_soundings('C2', cols=(0, args.cols) if args.cols else None, winds=False)
-    ncol = d['t'].shape[0]
-    rate0, _, _ = cpu_reference_rate(d, min(ncol, 4000 * nth), nth)
-    sample = int(min(ncol, max(2000 * nth, rate0 * args.ref_seconds)))
+    d = wl.make(0, args.cols)
+    rate0, _, _ = wl.cpu_rate(d, min(wl.ncol, 4000 * nth), nth)
+    sample = int(min(wl.ncol, max(2000 * nth, rate0 * args.ref_seconds)))
     for _ in range(args.warmup):
-        cpu_reference_rate(d, sample, nth)
+        wl.cpu_rate(d, sample, nth)
     t0 = time.perf_counter()
     n_done = 0
     for _ in range(args.steps):
-        _, _, n = cpu_reference_rate(d, sample, nth)
+        _, n, how = wl.cpu_rate(d, sample, nth)
         n_done += n
     dt = time.perf_counter() - t0
     v = n_done / dt
-    desc = f'{sample} of {ncol} columns per step (evenly strided), oracle tmode=LIBM, {nth} threads'
+    desc = f'{n} of {wl.ncol} columns per step (evenly strided), {how}, {nth} threads'
     print(json.dumps({
-        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'impl': 'reference', 'metric': wl.metric, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'sample': desc},
+        'config': {'workload': wl.workload, 'sample': desc},
         'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': nth, 'kind': 'port', 'sample': desc},
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}), flush=True)
 
@@ -154,6 +322,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
+    ap.add_argument('--workload', default='C2', choices=['C2', 'C3', 'C4', 'C5'])
     ap.add_argument('--cols', type=int, default=0, help='debug: use only the first COLS columns of the field')
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='CPU work budget of the cpu_baseline leg')
     ap.add_argument('--ref-seconds', type=float, default=3.0, help='CPU seconds per step of --impl reference')
@@ -164,15 +333,14 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
+    wl = get_workload(args.workload)
 
     if args.impl == 'reference':
-        return run_reference(args, rank, world)
+        return run_reference(args, rank, world, wl)
 
     import torch
     import torch.distributed as dist
     from xcape_b200 import _lib
-    from xcape_b200.cape_cuda import cape as cape_cuda, pres_lev_pos
-    from xcape_b200.synthetic import make_soundings
 
     if not torch.cuda.is_available() or _lib.device_count() < 1:
         raise SystemExit('bench.py: no CUDA device — the CUDA path has no CPU fallback')
@@ -180,6 +348,7 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # stdout carries exactly one JSON line
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():
@@ -195,16 +364,9 @@ def main():
         return float(t.item())
 
     # ---- this rank's field: time step `rank` of the synthetic stack -------------------------
-    d = make_soundings('C2', seed=2 + rank, cols=(0, args.cols) if args.cols else None, winds=False)
-    ncol, nlev = d['t'].shape
-    common = dict(flag_1d=1, source=2, ml_depth=500., adiabat=1, pinc=500., type_grid=2)
-
-    def run_cape(p, t2d, td2d, ps, ts, tds, plp=None, **kw):
-        return cape_cuda(p, t2d, td2d, ps, ts, tds, common['flag_1d'], plp, common['source'], common['ml_depth'],
-                         common['adiabat'], common['pinc'], common['type_grid'], **kw)
-
-    # device-resident copies, reference layout ([ncol, nlev], level last)
-    g = {k: torch.from_numpy(d[k]).to(dev) for k in ('p', 't', 'td', 'ps', 'ts', 'tds')}
+    d = wl.make(rank, args.cols)
+    ncol, nlev = wl.ncol, wl.nlev
+    g = wl.to_device(d, dev)       # device-resident, reference layout ([ncol, nlev], level last)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         # nvidia-smi's start-up (NVML init) stalls the GPU for tens of ms: let it reach its steady
@@ -215,22 +377,19 @@ def main():
             time.sleep(0.05)
     windows = []
 
-    def step_dev():
-        return run_cape(g['p'], g['t'].t(), g['td'].t(), g['ps'], g['ts'], g['tds'])
-
     for _ in range(args.warmup):
-        step_dev()
+        wl.step_dev(g)
     barrier()
     t_warm = time.time()
     while time.time() - t_warm < 0.5:      # clocks / power state settled (untimed)
-        step_dev()
+        wl.step_dev(g)
     barrier()
     l0 = _lib.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.time()
     e0.record()
     for _ in range(args.steps):
-        out_dev = step_dev()
+        out_dev = wl.step_dev(g)
     e1.record()
     barrier()
     windows.append((w0, time.time()))
@@ -238,52 +397,40 @@ def main():
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     value = world * ncol / (ms_step * 1e-3)
 
-    # ---- roofline leg: the CAPE kernel alone (level-major input, start precomputed) ---------
-    tm = g['t'].t().contiguous()
-    tdm = g['td'].t().contiguous()
-    plp = pres_lev_pos(g['p'], g['ps'])
-    cnt = run_cape(g['p'], tm, tdm, g['ps'], g['ts'], g['tds'], plp, return_counters=True)
-    total_iter = float(cnt[5].to(torch.float64).sum().item())
+    # ---- roofline leg: the dominant kernel alone (level-major input, one launch per step) -----
+    st = wl.kernel_state(g)
     for _ in range(3):
-        run_cape(g['p'], tm, tdm, g['ps'], g['ts'], g['tds'], plp)
+        wl.step_kernel(g, st)
     torch.cuda.synchronize()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lk = _lib.kernel_launches()
     w0 = time.time()
     k0.record()
     for _ in range(args.steps):
-        run_cape(g['p'], tm, tdm, g['ps'], g['ts'], g['tds'], plp)
+        wl.step_kernel(g, st)
     k1.record()
     torch.cuda.synchronize()
     windows.append((w0, time.time()))
     assert _lib.kernel_launches() - lk == args.steps, 'roofline leg must be exactly one kernel per step'
     ms_kernel = k0.elapsed_time(k1) / args.steps
-    del tm, tdm
+    st = {k: v for k, v in st.items() if not hasattr(v, 'is_cuda')}     # drop the level-major copies
 
     # ---- end to end: pinned host buffers through the host-pointer C-ABI call ------------------
-    pin = {k: torch.empty(d[k].shape, dtype=torch.float32).pin_memory() for k in ('t', 'td', 'ps', 'ts', 'tds')}
-    for k in pin:
-        pin[k].numpy()[...] = d[k]
-    hp = {k: v.numpy() for k, v in pin.items()}
-
-    def step_e2e():
-        return run_cape(d['p'], hp['t'].T, hp['td'].T, hp['ps'], hp['ts'], hp['tds'], device=local_rank)
-
+    hp = wl.pinned(d)
     for _ in range(2):
-        out_host = step_e2e()
+        out_host = wl.step_e2e(hp, local_rank)
     barrier()
     w0 = time.time()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out_host = step_e2e()
+        out_host = wl.step_e2e(hp, local_rank)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
     barrier()
     windows.append((w0, time.time()))
     e2e_value = world * ncol / e2e_s
-    h2d = int(2 * ncol * nlev * 4 + 3 * ncol * 4 + nlev * 4)
-    d2h = int(16 * ncol)
-    same = all(np.array_equal(a, b.cpu().numpy()) for a, b in zip(out_host, out_dev))
+    h2d, d2h = wl.io_bytes()
+    same = all(np.array_equal(np.asarray(a), b.cpu().numpy()) for a, b in zip(out_host, out_dev))
 
     clocks = sampler.stop(windows) if rank == 0 else None
 
@@ -294,34 +441,24 @@ def main():
         hbm_peak, hbm_src = 6650.0, 'fallback (B200_PROFILING.md)'
         if os.path.exists(peaks_file):
             hbm_peak, hbm_src = float(json.load(open(peaks_file))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
-        achieved_tf = FLOP_PER_ITER * total_iter / (ms_kernel * 1e-3) / 1e12
-        achieved_gbs = BYTES_PER_COL * ncol / (ms_kernel * 1e-3) / 1e9
-        roofline = {
-            'bound': 'fp32', 'achieved': achieved_tf, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': achieved_tf / fp32_peak,
-            'traffic': None, 'kernel': 'cape_kernel<MathSpec,2,1,true>', 'kernel_ms': ms_kernel,
-            'work': f'{FLOP_PER_ITER:.0f} flop x {total_iter / ncol:.1f} moist iterations/column (counted by the kernel)',
-            'peak_source': 'FFMA microbenchmark on this GPU (xcape_cuda_measure_peaks), 2 flop/FMA',
-            'fp64_peak_tflops': fp64_peak, 'iterations_per_s': total_iter / (ms_kernel * 1e-3),
-            'hbm': {'bound': 'hbm', 'achieved': achieved_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved_gbs / hbm_peak,
-                    'bytes_per_column': BYTES_PER_COL, 'peak_source': hbm_src}}
+        roofline = wl.roofline(ms_kernel, st, fp32_peak, fp64_peak, hbm_peak, hbm_src)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             oracle.build()
             nth = host_threads()
-            r0, _, _ = cpu_reference_rate(d, min(ncol, 2000 * nth), nth)
+            r0, _, _ = wl.cpu_rate(d, min(ncol, 2000 * nth), nth)
             sample = int(min(ncol, max(1000 * nth, r0 * args.cpu_seconds)))
-            rate, it_cpu, n = cpu_reference_rate(d, sample, nth, counters=True)
+            rate, n, how = wl.cpu_rate(d, sample, nth, counters=True)
             cpu = {'value': rate, 'unit': UNIT, 'cores': nth, 'kind': 'port',
-                   'sample': f'{n} of {ncol} columns (evenly strided) of the same field, oracle tmode=LIBM '
-                             f'(reference algorithm, glibc libm), {nth} threads; {it_cpu:.1f} iterations/column'}
+                   'sample': f'{n} of {ncol} columns (evenly strided) of the same field, {how}, {nth} threads'}
         line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'metric': wl.metric, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'columns_per_gpu': ncol, 'levels': nlev, 'layout': 'level-last [ncol, nlev] float32 '
-                       '(reference layout), resident in HBM', 'precision': 'faithful (bit-exact vs oracle SPEC arithmetic)',
-                       'l2': f'inputs {2 * ncol * nlev * 4 / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)',
+            'config': {'workload': wl.workload, 'columns_per_gpu': ncol, 'levels': nlev, 'layout': 'level-last [ncol, nlev] float32 '
+                       '(reference layout), resident in HBM', 'precision': 'faithful (CAPE bit-exact vs oracle SPEC arithmetic)',
+                       'l2': f'inputs {h2d / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)',
                        'parallelism': f'{world} x independent column shards, no collective'},
             'clocks': clocks, 'gpu_launches': int(launches),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
