@@ -33,3 +33,15 @@ for i in range(3): rep(f'nvidia-smi steady rep {i}')
 p.terminate()
 print(p.stdout.read()[-600:])
 for i in range(2): rep(f'poller gone rep {i}')
+
+# --- does the stream-ordered pool reuse blocks across steps that are enqueued but not yet executed?
+torch.cuda.synchronize()
+free0 = torch.cuda.mem_get_info()[0]
+t0 = time.perf_counter()
+for i in range(300):
+    step()
+    if i in (0, 9, 49, 99, 199, 299):
+        print(f'enqueued {i+1:3d} steps: host {time.perf_counter()-t0:6.2f} s, device memory in use grew by {(free0 - torch.cuda.mem_get_info()[0])/1e9:6.2f} GB', flush=True)
+torch.cuda.synchronize()
+print(f'after sync: grew by {(free0 - torch.cuda.mem_get_info()[0])/1e9:6.2f} GB')
+for i in range(2): rep(f'after deep queue rep {i}')
