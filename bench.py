@@ -387,13 +387,16 @@ def main():
     l0 = _lib.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.time()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         out_dev = wl.step_dev(g)
+        marks[i].record()
     e1.record()
     barrier()
     windows.append((w0, time.time()))
     launches = _lib.kernel_launches() - l0
+    per_step = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     value = world * ncol / (ms_step * 1e-3)
 
@@ -460,6 +463,7 @@ def main():
                        '(reference layout), resident in HBM', 'precision': 'faithful (CAPE bit-exact vs oracle SPEC arithmetic)',
                        'l2': f'inputs {h2d / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)',
                        'parallelism': f'{world} x independent column shards, no collective'},
+            'ms_per_step_minmedmax': [float(np.min(per_step)), float(np.median(per_step)), float(np.max(per_step))],
             'clocks': clocks, 'gpu_launches': int(launches),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': e2e_s * 1e3, 'matches_device_path': bool(same)},
