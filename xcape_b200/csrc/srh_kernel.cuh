@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "xc_math_spec.cuh"
+
 namespace xc {
 
 template <class T>
@@ -54,12 +56,32 @@ constexpr double R = (double)287.04f, g = (double)-9.80665f, eps = (double)0.621
 constexpr double t0 = (double)273.15f, c1 = (double)6.112f, c2 = (double)53.49f, c3 = (double)5.09f;
 }  // namespace hc
 
+// binary64 quotient to <= 1 ulp: MUFU.RCP64H seed + two Newton steps (6 FP64 issue slots against
+// ~20 for the IEEE-rounded `/`).  The SRH chain is compared with the reference at 1e-6 m2/s2
+// (values ~1e2), i.e. it needs ~1e-9 relative accuracy, not a particular rounding.
+__device__ __forceinline__ double ddiv_fast(double a, double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  r = __fma_rn(__fma_rn(-b, r, 1.0), r, r);
+  r = __fma_rn(__fma_rn(-b, r, 1.0), r, r);
+  const double q = a * r;
+  return __fma_rn(__fma_rn(-b, q, a), r, q);
+}
+
+// Virtual temperature, stdheight_2D_model_lev.f90:104-125:
+//   E = 6.112 exp(53.49 - 6808/Td - 5.09 ln Td),  w = eps E/(P-E),  Tv = T (w+eps)/(eps (1+w)).
+// The last two lines are evaluated in the algebraically identical one-division form
+//   Tv = T P / (P - (1-eps) E);  exp / log are the SPEC binary64 cores (relative error < 2^-44).
 __device__ __forceinline__ double tvirt(double T, double Td, double P) {
   const double Tin = T + hc::t0;
   const double Tdin = Td + hc::t0;
-  const double E = hc::c1 * exp((hc::c2 - (6808 / Tdin) - hc::c3 * log(Tdin)));
-  const double w = hc::eps * (E / (P - E));
-  return Tin * ((w + hc::eps) / (hc::eps * (1 + w)));
+  const double x = hc::c2 - ddiv_fast(6808.0, Tdin) - hc::c3 * spec_log_d(Tdin);
+  const double E = hc::c1 * spec_exp_d(x);
+  return ddiv_fast(Tin * P, P - (1.0 - hc::eps) * E);
+}
+// one hypsometric step, f90:143,152:  H = Hp + (R (Tv+Tvp)/2 / g) ln(P/Pp), with ln(P/Pp) = ln P - ln Pp
+__device__ __forceinline__ double hyps_step(double Hp, double Tv, double Tvp, double lnP, double lnPp) {
+  return Hp + (hc::R * ((Tv + Tvp) * 0.5) * (1.0 / hc::g)) * (lnP - lnPp);
 }
 
 __device__ __forceinline__ double interp1(double y1, double y3, double x1, double x2, double x3) {  // SREH_model_lev.f90:123-129
@@ -95,7 +117,7 @@ __device__ bool srh_column(const SrhArgs<T>& a, int64_t c, int ks, SrhOut& o) {
   const int n3 = a.nlev - ks + 1;                 // 3-D levels used
   const double Ps = (double)a.ps[c];
   double Tvp = tvirt((double)a.ts[c], (double)a.tds[c], Ps);
-  double Hp = a.aglh0, Pp = Ps;
+  double Hp = a.aglh0, Pp = Ps, lnPp = spec_log_d(Ps);
   double up = (double)a.us[c], vp = (double)a.vs[c];
   float upf = (float)a.us[c], vpf = (float)a.vs[c], zpf = (float)a.aglh0;
 
@@ -112,14 +134,15 @@ __device__ bool srh_column(const SrhArgs<T>& a, int64_t c, int ks, SrhOut& o) {
   bool descending = false;
   if (EXACT) {
     // DINTERP2DZ orientation test Z(1) > Z(NZ) needs the top height first (f90:211-216)
-    double H = Hp, Tv0 = Tvp, P0 = Pp;
+    double H = Hp, Tv0 = Tvp, lnP0 = lnPp;
     for (int i = 0; i < n3; ++i) {
       const int lev = ks - 1 + i;
       const int64_t off = (int64_t)lev * a.ld + c;
       const double P = ld_p<T, P1D>(a, c, lev);
       const double Tv = tvirt((double)a.t[off], (double)a.td[off], P);
-      H = H + ((hc::R * ((Tv + Tv0) / 2) / hc::g)) * (log(P / P0));
-      Tv0 = Tv; P0 = P;
+      const double lnP = spec_log_d(P);
+      H = hyps_step(H, Tv, Tv0, lnP, lnP0);
+      Tv0 = Tv; lnP0 = lnP;
     }
     descending = ((float)a.aglh0 > (float)H);
   }
@@ -135,8 +158,8 @@ __device__ bool srh_column(const SrhArgs<T>& a, int64_t c, int ks, SrhOut& o) {
     if (!(P < Pp)) mono = false;
     const T uin = a.u[off], vin = a.v[off];
     const double Tv = tvirt((double)a.t[off], (double)a.td[off], P);
-    // stdheight_2D_model_lev.f90:143,152
-    const double H = Hp + ((hc::R * ((Tv + Tvp) / 2) / hc::g)) * (log(P / Pp));
+    const double lnP = spec_log_d(P);
+    const double H = hyps_step(Hp, Tv, Tvp, lnP, lnPp);        // stdheight_2D_model_lev.f90:143,152
     const double uk = (double)uin, vk = (double)vin;
     const float ukf = (float)uin, vkf = (float)vin, zkf = (float)H;
 
@@ -187,7 +210,7 @@ __device__ bool srh_column(const SrhArgs<T>& a, int64_t c, int ks, SrhOut& o) {
       S3 = S3 + du;
     }
 
-    Hp = H; Tvp = Tv; Pp = P; up = uk; vp = vk; upf = ukf; vpf = vkf; zpf = zkf;
+    Hp = H; Tvp = Tv; Pp = P; lnPp = lnP; up = uk; vp = vk; upf = ukf; vpf = vkf; zpf = zkf;
     if (!EXACT && found_top && j >= 13) { ++i; break; }   // nothing above can matter if p keeps decreasing
   }
   if (!EXACT) {
@@ -253,15 +276,16 @@ __global__ void __launch_bounds__(128) stdheight_kernel(const HeightArgs<T> a) {
   ks = ks < 1 ? 1 : (ks > a.nlev ? a.nlev : ks);
   for (int lev = 0; lev < ks - 1; ++lev) a.h[c * a.h_col_stride + lev * a.h_lev_stride] = -999999.0;   // pressure_lev.f90:85-87
   const double Ps = (double)a.ps[c];
-  double Tvp = tvirt((double)a.ts[c], (double)a.tds[c], Ps), Hp = a.aglh0, Pp = Ps;
+  double Tvp = tvirt((double)a.ts[c], (double)a.tds[c], Ps), Hp = a.aglh0, lnPp = spec_log_d(Ps);
   a.hs[c] = a.aglh0;
   for (int lev = ks - 1; lev < a.nlev; ++lev) {
     const int64_t off = (int64_t)lev * a.ld + c;
     const double P = (double)(P1D ? __ldg(a.p + lev) : a.p[off]);
     const double Tv = tvirt((double)a.t[off], (double)a.td[off], P);
-    const double H = Hp + ((hc::R * ((Tv + Tvp) / 2) / hc::g)) * (log(P / Pp));
+    const double lnP = spec_log_d(P);
+    const double H = hyps_step(Hp, Tv, Tvp, lnP, lnPp);
     a.h[c * a.h_col_stride + lev * a.h_lev_stride] = H;
-    Hp = H; Tvp = Tv; Pp = P;
+    Hp = H; Tvp = Tv; lnPp = lnP;
   }
 }
 
