@@ -43,7 +43,12 @@ enum { XCAPE_ADIABAT_PSEUDO_LIQUID = 1, XCAPE_ADIABAT_REVERSIBLE_LIQUID = 2,
        XCAPE_ADIABAT_PSEUDO_ICE = 3, XCAPE_ADIABAT_REVERSIBLE_ICE = 4 };                          /* core.py:303-304 */
 /* XCAPE_FAITHFUL: IEEE binary32 chain without FMA contraction + the deterministic "SPEC"
  * transcendentals of DESIGN.md (bit-identical to oracle tmode=SPEC).  Default. */
-enum { XCAPE_FAITHFUL = 0 };
+enum { XCAPE_FAITHFUL = 0,
+/* XCAPE_FAST (CAPE only): identical prep / source selection (MU level index stays exact); the
+ * moist fixed-point body runs on the FP32 pipe with FMAs, a ~1-ulp expf and MUFU reciprocals.
+ * CAPE / CIN then agree with the reference within max(1 J/kg, 1e-4 relative) except on
+ * ill-conditioned columns (non-convergence limit cycles, CIN sign flips). */
+       XCAPE_FAST = 1 };
 /* per-column status word (optional output) */
 enum { XCAPE_ST_OK = 0, XCAPE_ST_SKIPPED = 1 /* ts <= 0 degC gate, f90:77 */,
        XCAPE_ST_NONCONVERGED = 2 /* > 100 moist iterations, f90:464-474: cape = cin = 0 */ };

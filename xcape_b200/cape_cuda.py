@@ -16,7 +16,8 @@ from .sharding import column_blocks, run_on_devices
 
 
 def cape(p_2d, t_2d, td_2d, p_s, t_s, td_s, flag_1d, pres_lev_pos, source, ml_depth, adiabat, pinc,
-         type_grid, *, device=0, devices=None, stream=None, return_status=False, return_counters=False):
+         type_grid, *, device=0, devices=None, stream=None, precision='faithful', return_status=False,
+         return_counters=False):
     """
     Parameters follow ``cape_fortran.cape`` (cape_fortran.py:5-46): ``*_2d`` are
     ``(nlev, ngrid)`` (``p_2d`` is ``(nlev, 1)`` / ``(nlev,)`` when ``flag_1d == 1``), ``*_s`` are
@@ -27,7 +28,9 @@ def cape(p_2d, t_2d, td_2d, p_s, t_s, td_s, flag_1d, pres_lev_pos, source, ml_de
 
     Extra keyword-only arguments: ``device`` (CUDA ordinal for host inputs), ``devices`` (list:
     shard host inputs in contiguous column blocks over several GPUs), ``stream`` (raw
-    ``cudaStream_t`` for device inputs; default torch's current stream), ``return_status``
+    ``cudaStream_t`` for device inputs; default torch's current stream), ``precision``
+    (``'faithful'``: bit-identical to the oracle's SPEC arithmetic; ``'fast'``: FP32-pipe moist
+    iteration, tolerance-level parity, MU level still exact), ``return_status``
     (append the per-column status word), ``return_counters`` (append status and the number of
     moist-adiabat iterations each column ran).
 
@@ -35,6 +38,9 @@ def cape(p_2d, t_2d, td_2d, p_s, t_s, td_s, flag_1d, pres_lev_pos, source, ml_de
     — numpy arrays for host inputs, torch CUDA tensors for CUDA-tensor inputs.
     """
     L = _lib.lib()
+    if precision not in _lib.PRECISION:
+        raise ValueError(f"precision must be one of {list(_lib.PRECISION)}")
+    prec = _lib.PRECISION[precision]
     nlev, ngrid = t_2d.shape
     if type_grid == 1:
         p_is_1d = 0
@@ -97,7 +103,7 @@ def cape(p_2d, t_2d, td_2d, p_s, t_s, td_s, flag_1d, pres_lev_pos, source, ml_de
             C.c_int64(n), nlev, p_is_1d, dt, layout, mem, int(source), int(adiabat),
             C.c_float(float(ml_depth)), C.c_float(float(pinc)), off1(start, 4),
             off1(cape_o, 4), off1(cin_o, 4), off1(mu_o, 4), off1(z_o, 4), off1(st_o, 4), off1(it_o, 4),
-            _lib.FAITHFUL, dev, A.stream_of(ref, stream))
+            prec, dev, A.stream_of(ref, stream))
         _lib.check(rc)
 
     if mem == _lib.MEM_HOST and devices is not None and len(devices) > 1:

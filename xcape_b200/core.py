@@ -22,7 +22,8 @@ forwards to an installed reference ``xcape`` if there is one); ``calc_srh`` gain
 ``vertical_lev`` may be omitted (defaults to ``'sigma'`` as the reference's docstring promises but
 its code does not, core.py:229); inputs may be torch CUDA tensors (results are then CUDA tensors);
 ``lev_axis=0`` accepts level-major ``[nlev, ...]`` arrays (the on-disk order of ERA5 / HRRR) with
-zero relayout; ``device=`` / ``devices=[...]`` pick the GPU(s).
+zero relayout; ``device=`` / ``devices=[...]`` pick the GPU(s); ``calc_cape(precision='fast')`` trades
+bit-exactness of CAPE/CIN for about twice the speed (tolerance-level parity, MU level still exact).
 """
 from functools import reduce
 
@@ -164,7 +165,7 @@ def _calc_cape_gufunc(*args, **kwargs):
 
 def _calc_cape_numpy(*args, source='surface', ml_depth=500., adiabat='pseudo-liquid', pinc=500.,
                      method='cuda', vertical_lev='sigma', lev_axis=-1, device=0, devices=None,
-                     stream=None):
+                     stream=None, precision='faithful'):
     """Flatten to columns, dispatch on ``method``, restore the grid shape (core.py:261-332)."""
     p, t, td, ps, ts, tds = (_as_array(a) for a in args)
     lev_axis = 0 if lev_axis == 0 else -1
@@ -190,7 +191,7 @@ def _calc_cape_numpy(*args, source='surface', ml_depth=500., adiabat='pseudo-liq
         from .cape_cuda import cape as _cape_cuda
         # pres_lev_pos=None: computed on the device instead of core.py:286-289's numpy temporaries
         outs = _cape_cuda(p_2d, t_2d, td_2d, p_s1d, t_s1d, td_s1d, flag_1d, None, **opts,
-                          device=device, devices=devices, stream=stream)
+                          device=device, devices=devices, stream=stream, precision=precision)
     elif method in ('fortran', 'dummy'):
         host = [A.to_host_numpy(a) for a in (p_2d, t_2d, td_2d, p_s1d, t_s1d, td_s1d)]
         if method == 'dummy':

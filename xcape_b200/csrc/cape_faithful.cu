@@ -1,4 +1,5 @@
-// cape_faithful.cu — instantiations of the CAPE kernel with the FAITHFUL math policy.
+// cape_faithful.cu — instantiations of the CAPE kernel with the FAITHFUL math policy
+// (and, compiled a second time with -DXC_FAST_TU as build/cape_fast.o, with the FAST moist body).
 // Compiled with -fmad=false -prec-div=true -prec-sqrt=true -ftz=false: every binary32
 // operation is an individually rounded IEEE operation, exactly like the reference built by
 // gfortran -O3 on x86-64 (no FMA contraction).
@@ -9,18 +10,29 @@
 namespace xc {
 
 struct MathSpec {
+  static constexpr bool kFastBody = false;
   static __device__ __forceinline__ float exp(float x) { return spec_expf(x); }
   static __device__ __forceinline__ float exp_small(float x) { return spec_expf_small(x); }
   static __device__ __forceinline__ float log(float x) { return spec_logf(x); }
   static __device__ __forceinline__ float pow(float x, float y) { return spec_powf(x, y); }
 };
 
+#ifdef XC_FAST_TU
+// Same SPEC prep arithmetic (so source selection / MU index stay bit-exact), FAST moist body.
+struct MathFast : MathSpec { static constexpr bool kFastBody = true; };
+using MathPolicy = MathFast;
+#define XC_LAUNCH_NAME launch_cape_fast
+#else
+using MathPolicy = MathSpec;
+#define XC_LAUNCH_NAME launch_cape_faithful
+#endif
+
 template <int SOURCE, int ADIABAT, bool P1D>
 static int launch(const CapeArgs& a, cudaStream_t s) {
   const int threads = 128;
   const int64_t blocks = (a.ncol + threads - 1) / threads;
   if (blocks <= 0) return XCAPE_OK;
-  cape_kernel<MathSpec, SOURCE, ADIABAT, P1D><<<(unsigned)blocks, threads, 0, s>>>(a);
+  cape_kernel<MathPolicy, SOURCE, ADIABAT, P1D><<<(unsigned)blocks, threads, 0, s>>>(a);
   XC_LAUNCH_CHECK();
   return XCAPE_OK;
 }
@@ -36,7 +48,7 @@ static int launch_adiabat(const CapeArgs& a, int adiabat, cudaStream_t s) {
   return fail(XCAPE_ERR_ARG, "adiabat must be 1..4");
 }
 
-int launch_cape_faithful(const CapeArgs& a, int source, int adiabat, bool p1d, cudaStream_t s) {
+int XC_LAUNCH_NAME(const CapeArgs& a, int source, int adiabat, bool p1d, cudaStream_t s) {
   switch (source) {
     case 1: return p1d ? launch_adiabat<1, true>(a, adiabat, s) : launch_adiabat<1, false>(a, adiabat, s);
     case 2: return p1d ? launch_adiabat<2, true>(a, adiabat, s) : launch_adiabat<2, false>(a, adiabat, s);
