@@ -107,6 +107,8 @@ class CapeWorkload:
     """calc_cape on a named synthetic configuration."""
     kind = 'cape'
 
+    precision = 'faithful'
+
     def __init__(self, cfg, source, ml_depth, metric, workload):
         self.cfg, self.source, self.ml_depth = cfg, source, float(ml_depth)
         self.src_id = {'surface': 1, 'most-unstable': 2, 'mixed-layer': 3}[source]
@@ -129,6 +131,7 @@ class CapeWorkload:
 
     def _call(self, p, t2, td2, ps, ts, tds, plp, **kw):
         from xcape_b200.cape_cuda import cape
+        kw.setdefault('precision', self.precision)
         return cape(p, t2, td2, ps, ts, tds, 1 if self.p1d else 0, plp, self.src_id, self.ml_depth, 1, 500.,
                     2 if self.p1d else 1, **kw)
 
@@ -149,8 +152,8 @@ class CapeWorkload:
         st['total_iter'] = float(cnt[5].double().sum().item())
         return st
 
-    def step_kernel(self, g, st):
-        return self._call(st['p'], st['t'], st['td'], g['ps'], g['ts'], g['tds'], st['plp'])
+    def step_kernel(self, g, st, **kw):
+        return self._call(st['p'], st['t'], st['td'], g['ps'], g['ts'], g['tds'], st['plp'], **kw)
 
     def pinned(self, d):
         import torch
@@ -327,6 +330,8 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='CPU work budget of the cpu_baseline leg')
     ap.add_argument('--ref-seconds', type=float, default=3.0, help='CPU seconds per step of --impl reference')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--precision', default='faithful', choices=['faithful', 'fast'],
+                    help="CAPE arithmetic of every timed leg (default: faithful = bit-exact vs the oracle's SPEC mode)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'cuda' else args.warmup
 
@@ -334,6 +339,7 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     wl = get_workload(args.workload)
+    wl.precision = args.precision
 
     if args.impl == 'reference':
         return run_reference(args, rank, world, wl)
@@ -416,6 +422,29 @@ def main():
     windows.append((w0, time.time()))
     assert _lib.kernel_launches() - lk == args.steps, 'roofline leg must be exactly one kernel per step'
     ms_kernel = k0.elapsed_time(k1) / args.steps
+    other = None
+    if wl.kind == 'cape':        # the other precision mode, kernel only, for the record
+        alt = 'fast' if args.precision == 'faithful' else 'faithful'
+        for _ in range(3):
+            wl.step_kernel(g, st, precision=alt)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(args.steps):
+            out_alt = wl.step_kernel(g, st, precision=alt)
+        a1.record()
+        torch.cuda.synchronize()
+        ms_alt = a0.elapsed_time(a1) / args.steps
+        ref_k = wl.step_kernel(g, st)
+        dc = (out_alt[0] - ref_k[0]).abs()
+        lim = torch.clamp(1e-4 * ref_k[0].abs(), min=1.0)
+        lim_i = torch.clamp(1e-4 * ref_k[1].abs(), min=1.0)
+        other = {'precision': alt, 'kernel_ms': ms_alt, 'kernel_columns_per_s': ncol / (ms_alt * 1e-3),
+                 'vs_' + args.precision: {'columns': ncol,
+                                          'cape_or_cin_outside_max(1,1e-4rel)': int(((dc > lim) | ((out_alt[1] - ref_k[1]).abs() > lim_i)).sum().item()),
+                                          'max_abs_dcape': float(dc.max().item()), 'mean_abs_dcape': float(dc.mean().item()),
+                                          'mulev_differs': int((out_alt[2] != ref_k[2]).sum().item())}}
+        del out_alt, ref_k
     st = {k: v for k, v in st.items() if not hasattr(v, 'is_cuda')}     # drop the level-major copies
 
     # ---- end to end: pinned host buffers through the host-pointer C-ABI call ------------------
@@ -460,14 +489,15 @@ def main():
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
             'config': {'workload': wl.workload, 'columns_per_gpu': ncol, 'levels': nlev, 'layout': 'level-last [ncol, nlev] float32 '
-                       '(reference layout), resident in HBM', 'precision': 'faithful (CAPE bit-exact vs oracle SPEC arithmetic)',
+                       '(reference layout), resident in HBM', 'precision': args.precision + (' (CAPE bit-exact vs oracle SPEC arithmetic)' if args.precision == 'faithful' else
+                                                     ' (FP32-pipe moist body; tolerance-level parity, MU level exact)'),
                        'l2': f'inputs {h2d / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)',
                        'parallelism': f'{world} x independent column shards, no collective'},
             'ms_per_step_minmedmax': [float(np.min(per_step)), float(np.median(per_step)), float(np.max(per_step))],
             'clocks': clocks, 'gpu_launches': int(launches),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': e2e_s * 1e3, 'matches_device_path': bool(same)},
-            'roofline': roofline, 'cpu_baseline': cpu}
+            'roofline': roofline, 'cpu_baseline': cpu, 'other_precision': other}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
