@@ -374,7 +374,7 @@ def main():
     ncol, nlev = wl.ncol, wl.nlev
     g = wl.to_device(d, dev)       # device-resident, reference layout ([ncol, nlev], level last)
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get('XCAPE_BENCH_NO_SAMPLER'):
         # nvidia-smi's start-up (NVML init) stalls the GPU for tens of ms: let it reach its steady
         # sampling state before anything is timed
         sampler.start()
@@ -464,7 +464,7 @@ def main():
     h2d, d2h = wl.io_bytes()
     same = all(np.array_equal(np.asarray(a), b.cpu().numpy()) for a, b in zip(out_host, out_dev))
 
-    clocks = sampler.stop(windows) if rank == 0 else None
+    clocks = sampler.stop(windows) if (rank == 0 and sampler.proc is not None) else None
 
     # ---- peaks + CPU baseline (rank 0) ---------------------------------------------------------
     if rank == 0:
@@ -494,6 +494,7 @@ def main():
                        'l2': f'inputs {h2d / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)',
                        'parallelism': f'{world} x independent column shards, no collective'},
             'ms_per_step_minmedmax': [float(np.min(per_step)), float(np.median(per_step)), float(np.max(per_step))],
+            'ms_each_step': [round(float(x), 3) for x in per_step],
             'clocks': clocks, 'gpu_launches': int(launches),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': e2e_s * 1e3, 'matches_device_path': bool(same)},
