@@ -29,6 +29,7 @@ Numbers on the JSON line:
              all host threads over a bounded sample of the same field (rank 0, N = 1).
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -390,6 +391,10 @@ def main():
     while time.time() - t_warm < 0.5:      # clocks / power state settled (untimed)
         wl.step_dev(g)
     barrier()
+    # Python's cyclic GC can pause the enqueuing thread for 40-90 ms in the middle of a step (seen as
+    # one slow step in ~1 of 3 runs); like timeit, collect first and keep it off while timing.
+    gc.collect()
+    gc.disable()
     l0 = _lib.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.time()
@@ -464,6 +469,7 @@ def main():
     h2d, d2h = wl.io_bytes()
     same = all(np.array_equal(np.asarray(a), b.cpu().numpy()) for a, b in zip(out_host, out_dev))
 
+    gc.enable()
     clocks = sampler.stop(windows) if (rank == 0 and sampler.proc is not None) else None
 
     # ---- peaks + CPU baseline (rank 0) ---------------------------------------------------------
