@@ -235,8 +235,11 @@ inline int64_t env_i64(const char* name, int64_t dflt, int64_t lo, int64_t hi) {
   }
   return dflt;
 }
-// Tunables of the host-pointer path (columns per staged block, streams in the ring).
-inline int64_t chunk_cols() { return env_i64("XCAPE_B200_CHUNK_COLS", 1 << 17, 1024, 1 << 26); }
+// Tunables of the host-pointer path (columns per staged block, streams in the ring).  Blocks
+// grow geometrically from XCAPE_B200_FIRST_CHUNK_COLS to XCAPE_B200_CHUNK_COLS: a small first block
+// gets the GPU busy after ~0.3 ms of H2D, large later blocks keep per-kernel tails rare.
+inline int64_t chunk_cols() { return env_i64("XCAPE_B200_CHUNK_COLS", 1 << 19, 1024, 1 << 26); }
+inline int64_t first_chunk_cols() { return env_i64("XCAPE_B200_FIRST_CHUNK_COLS", 1 << 15, 1024, 1 << 26); }
 inline int ring_streams() { return (int)env_i64("XCAPE_B200_STREAMS", 4, 1, kMaxStreams); }
 
 struct HostIn3 { const void* host; };                    // [ncol][nlev] or [nlev][ncol], es bytes/element
@@ -298,8 +301,11 @@ bool is_pageable_host(const void* p) {
 template <class F>
 int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_host, const std::vector<HostIn3>& in3,
                const std::vector<HostIn1>& in1, const std::vector<HostOut>& outs, F launch) {
-  const int64_t chunk = std::min<int64_t>(ncol, chunk_cols());
-  const int nstream = (int)std::min<int64_t>(ring_streams(), (ncol + chunk - 1) / chunk);
+  const int64_t chunk = std::min<int64_t>(ncol, chunk_cols());          // capacity of a slot
+  const int64_t first = std::min<int64_t>(chunk, first_chunk_cols());
+  int nblocks = 0;
+  for (int64_t c = 0, n = first; c < ncol; c += n, n = std::min<int64_t>(chunk, n * 2)) ++nblocks;
+  const int nstream = std::min<int>(ring_streams(), nblocks);
   cudaStream_t st[kMaxStreams] = {};
   cudaEvent_t done[kMaxStreams] = {};
   Block b[kMaxStreams];
@@ -341,8 +347,10 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
       }
     }
     int i = 0;
-    for (int64_t c0 = 0; c0 < ncol; c0 += chunk, i = (i + 1) % nstream) {
-      const int64_t n = std::min<int64_t>(chunk, ncol - c0);
+    int64_t want = first;
+    for (int64_t c0 = 0; c0 < ncol; i = (i + 1) % nstream) {
+      const int64_t n = std::min<int64_t>(want, ncol - c0);
+      want = std::min<int64_t>(chunk, want * 2);
       cudaStream_t s = st[i];
       int r = drain(i);                            // slot reuse: its previous block must have left
       if (r) return r;
@@ -358,6 +366,7 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
       }
       XC_CUDA(cudaEventRecord(done[i], s));
       pend[i].on = true; pend[i].c0 = c0; pend[i].n = n;
+      c0 += n;
     }
     for (int k = 0; k < nstream; ++k) {            // oldest block first
       int r = drain((i + k) % nstream);
