@@ -11,18 +11,19 @@ if len(sys.argv) > 1 and sys.argv[1] == 'child':
     pin = {k: torch.empty(d[k].shape, dtype=torch.float32).pin_memory() for k in ('t', 'td', 'ps', 'ts', 'tds')}
     for k in pin: pin[k].numpy()[...] = d[k]
     hp = {k: v.numpy() for k, v in pin.items()}
-    f = lambda: cape(d['p'], hp['t'].T, hp['td'].T, hp['ps'], hp['ts'], hp['tds'], 1, None, 2, 500., 1, 500., 2)
+    prec = os.environ.get('PREC', 'faithful')
+    f = lambda: cape(d['p'], hp['t'].T, hp['td'].T, hp['ps'], hp['ts'], hp['tds'], 1, None, 2, 500., 1, 500., 2, precision=prec)
     for _ in range(3): f()
     t0 = time.perf_counter()
     for _ in range(10): f()
     dt = (time.perf_counter() - t0) / 10
     # pageable input for comparison
-    g = lambda: cape(d['p'], d['t'].T, d['td'].T, d['ps'], d['ts'], d['tds'], 1, None, 2, 500., 1, 500., 2)
-    for _ in range(2): g()
+    g = lambda: cape(d['p'], d['t'].T, d['td'].T, d['ps'], d['ts'], d['tds'], 1, None, 2, 500., 1, 500., 2, precision=prec)
+    for _ in range(1): g()
     t0 = time.perf_counter()
-    for _ in range(5): g()
-    dp = (time.perf_counter() - t0) / 5
-    print(f"chunk={os.environ.get('XCAPE_B200_CHUNK_COLS')} streams={os.environ.get('XCAPE_B200_STREAMS')}: pinned {dt*1e3:.2f} ms/field ({d['t'].shape[0]/dt/1e6:.1f} Mcol/s)  pageable {dp*1e3:.2f} ms/field")
+    for _ in range(3): g()
+    dp = (time.perf_counter() - t0) / 3
+    print(f"chunk={os.environ.get('XCAPE_B200_CHUNK_COLS')} first={os.environ.get('XCAPE_B200_FIRST_CHUNK_COLS')} streams={os.environ.get('XCAPE_B200_STREAMS')}: pinned {dt*1e3:.2f} ms/field ({d['t'].shape[0]/dt/1e6:.1f} Mcol/s)  pageable {dp*1e3:.2f} ms/field")
     sys.exit(0)
 
 x = torch.empty(320 * 1024 * 1024 // 4, dtype=torch.float32).pin_memory()
@@ -37,6 +38,6 @@ for _ in range(5): x.copy_(y, non_blocking=True)
 torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
 print(f'D2H pinned 320 MiB: {dt*1e3:.2f} ms  ({x.numel()*4/dt/1e9:.1f} GB/s)')
 del x, y
-for chunk, streams in ((262144, 3), (131072, 4), (65536, 4), (32768, 4), (65536, 8), (131072, 2), (1048576, 1)):
-    env = dict(os.environ, XCAPE_B200_CHUNK_COLS=str(chunk), XCAPE_B200_STREAMS=str(streams))
+for chunk, first, streams in ((524288, 32768, 4), (524288, 65536, 4), (262144, 32768, 4), (1048576, 32768, 4), (524288, 16384, 4), (131072, 131072, 4), (524288, 32768, 3)):
+    env = dict(os.environ, XCAPE_B200_CHUNK_COLS=str(chunk), XCAPE_B200_FIRST_CHUNK_COLS=str(first), XCAPE_B200_STREAMS=str(streams))
     print(subprocess.run([sys.executable, __file__, 'child'], env=env, capture_output=True, text=True).stdout.strip())
