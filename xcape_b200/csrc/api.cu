@@ -2,6 +2,7 @@
 // canonicalisation of dtype/layout on the device, kernel dispatch, and the host-pointer
 // path (column blocks staged H2D / computed / D2H on a ring of streams).
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -315,6 +316,9 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
   for (size_t k = 0; k < outs.size(); ++k)
     staged[k] = (outs[k].host && !outs[k].is3d && is_pageable_host(outs[k].host)) ? 1 : 0;
 
+  const bool trace = getenv("XCAPE_B200_TRACE") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
   auto drain = [&](int i) -> int {                // wait for slot i's block, hand its outputs to the caller
     if (!pend[i].on) return XCAPE_OK;
     XC_CUDA(cudaEventSynchronize(done[i]));
@@ -346,6 +350,7 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
         XC_CUDA(cudaMemcpyAsync(b[i].p1d, p1d_host, (size_t)nlev * es, cudaMemcpyHostToDevice, st[i]));
       }
     }
+    if (trace) fprintf(stderr, "[xcape_b200]   setup done at %.3f ms\n", now() - t_begin);
     int i = 0;
     int64_t want = first;
     for (int64_t c0 = 0; c0 < ncol; i = (i + 1) % nstream) {
@@ -368,14 +373,17 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
       pend[i].on = true; pend[i].c0 = c0; pend[i].n = n;
       c0 += n;
     }
+    if (trace) fprintf(stderr, "[xcape_b200]   all blocks enqueued at %.3f ms\n", now() - t_begin);
     for (int k = 0; k < nstream; ++k) {            // oldest block first
       int r = drain((i + k) % nstream);
       if (r) return r;
+      if (trace) fprintf(stderr, "[xcape_b200]   slot %d drained at %.3f ms\n", (i + k) % nstream, now() - t_begin);
     }
     for (int k = 0; k < nstream; ++k) XC_CUDA(cudaStreamSynchronize(st[k]));
     return XCAPE_OK;
   };
   int rc = body();
+  const double t_body = now();
   std::string keep = g_last_error;
   for (int i = 0; i < nstream; ++i) {
     if (st[i]) {
@@ -390,6 +398,8 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
     for (void* h : stage[i]) if (h) g_pinned.release(h);
   }
   if (rc) { cudaGetLastError(); g_last_error = keep; }
+  if (trace) fprintf(stderr, "[xcape_b200] run_staged ncol=%lld blocks=%d streams=%d: body %.3f ms, teardown %.3f ms\n",
+                     (long long)ncol, nblocks, nstream, t_body - t_begin, now() - t_body);
   return rc;
 }
 
