@@ -194,7 +194,8 @@ class CapeWorkload:
         tf = FLOP_PER_ITER * st['total_iter'] / (ms_kernel * 1e-3) / 1e12
         gbs = self.bytes_per_col * self.ncol / (ms_kernel * 1e-3) / 1e9
         return {
-            'bound': 'fp32', 'achieved': tf, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': tf / fp32_peak, 'traffic': None,
+            'bound': 'fp32', 'achieved': tf, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': tf / fp32_peak,
+            'traffic': ncu_traffic(f'cape_{self.cfg}_{self.precision}', self.ncol),
             'kernel': f'cape_kernel<MathSpec,{self.src_id},1,{str(self.p1d).lower()}>', 'kernel_ms': ms_kernel,
             'work': f"{FLOP_PER_ITER:.0f} flop x {st['total_iter'] / self.ncol:.1f} moist iterations/column (counted by the kernel)",
             'peak_source': 'FFMA microbenchmark on this GPU (xcape_cuda_measure_peaks), 2 flop/FMA',
@@ -269,10 +270,21 @@ class SrhWorkload:
 
     def roofline(self, ms_kernel, st, fp32_peak, fp64_peak, hbm_peak, hbm_src):
         gbs = self.bytes_per_col * self.ncol / (ms_kernel * 1e-3) / 1e9
-        return {'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak, 'traffic': None,
+        return {'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
+                'traffic': ncu_traffic('srh_' + self.cfg, self.ncol),
                 'kernel': 'srh_kernel<float,false>', 'kernel_ms': ms_kernel, 'bytes_per_column': self.bytes_per_col,
                 'peak_source': hbm_src, 'fp64_peak_tflops': fp64_peak,
                 'note': 'faithful mode evaluates the hypsometric exp/log chain in binary64 (reference arithmetic)'}
+
+
+def ncu_traffic(key, ncol):
+    """DRAM bytes per launch from the committed ncu capture of the same kernel (profiles/ncu_traffic.json)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))[key]
+        return {'bytes_per_launch': t['dram_bytes_per_column'] * ncol, 'bytes_per_column': t['dram_bytes_per_column'],
+                'source': t['source']}
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def get_workload(name):
