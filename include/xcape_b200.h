@@ -100,6 +100,18 @@ int xcape_cuda_srh(const void* p, const void* t, const void* td, const void* u, 
                    double* srh_rm, double* srh_lm, float* rm, float* lm, float* mean6,
                    int precision, int device, void* stream);
 
+/* The reference's two-call form: heights already computed (by xcape_cuda_stdheight or by the
+ * caller).  Replaces bunkers_loop_ml / bunkers_loop_pl + loop_sreh_ml / loop_sreh_pl exactly as
+ * srh.srh chains them (srh.py:41-61): u, v, aglh 3-D fields, us, vs, aglhs [ncol]; levels below
+ * start_3d (NULL = 1) are ignored.  Heights are used as binary64 by the helicity sum and
+ * down-cast to binary32 by the Bunkers part, like the f2py casts do. */
+int xcape_cuda_srh_from_heights(const void* u, const void* v, const void* aglh,
+                                const void* us, const void* vs, const void* aglhs,
+                                int64_t ncol, int nlev, int dtype, int layout, int mem,
+                                double depth, const int32_t* start_3d,
+                                double* srh_rm, double* srh_lm, float* rm, float* lm, float* mean6,
+                                int device, void* stream);
+
 /* Heights only (loop_stdheight_ml / loop_stdheight_pl1d).  h is float64, same layout as the
  * inputs' `layout`; levels below start_3d are -999999 (stdheight_2D_pressure_lev.f90:85-87);
  * hs [ncol] = aglh0. */

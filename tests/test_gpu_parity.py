@@ -290,6 +290,30 @@ def test_srh_vs_oracle(core, oracle_mod, cfg, vertical_lev, dtype):
             assert np.abs(g - r).max() <= 2e-5, np.abs(g - r).max()
 
 
+@pytest.mark.parametrize('cfg,type_grid', [('C3', 1), ('C2', 2)])
+def test_srh_two_call_form_matches_fused_and_oracle(core, oracle_mod, cfg, type_grid):
+    """The reference's own call sequence (core.py:516-535): stdheight(...) then srh(u, v, aglh, ...),
+    here through stdheight_cuda.stdheight + srh_cuda.srh, against the fused kernel and the oracle."""
+    from xcape_b200.srh_cuda import srh as srh_two_call
+    from xcape_b200.stdheight_cuda import stdheight
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings(cfg, cols=(0, 10000))
+    p2 = d['p'] if type_grid == 2 else d['p'].T
+    plp = oracle_mod.pres_lev_pos(d['ps'], d['p'][:, None]) if type_grid == 2 else 1
+    H, Hs = stdheight(p2, d['t'].T, d['td'].T, d['ps'], d['ts'], d['tds'], 1 if type_grid == 2 else 0, plp, 2., type_grid)
+    Ho, Hso = oracle_mod.stdheight(p2 if type_grid == 1 else p2[:, None], d['t'].T, d['td'].T, d['ps'], d['ts'], d['tds'],
+                                   1 if type_grid == 2 else 0, plp, 2., type_grid)
+    assert np.abs(np.asarray(H) - Ho).max() < 1e-6 and np.array_equal(Hs, Hso)
+    two = srh_two_call(d['u'].T, d['v'].T, H, d['us'], d['vs'], Hs, plp, 3000, type_grid, 2)
+    ref = oracle_mod.srh(d['u'].T, d['v'].T, Ho, d['us'], d['vs'], Hso, plp, 3000, type_grid, 2)
+    fused = core.calc_srh(*(d[k] for k in ('p', 't', 'td', 'u', 'v', 'ps', 'ts', 'tds', 'us', 'vs')), depth=3000,
+                          vertical_lev='sigma' if type_grid == 1 else 'pressure', output_var='srh', method='cuda')
+    for g, r, f in zip(two[:2], ref[:2], fused):
+        assert np.abs(g - r).max() <= 1e-6 and np.abs(g - f).max() <= 1e-6
+    for g, r in zip(two[2:], ref[2:]):
+        assert np.abs(np.asarray(g) - r).max() <= 2e-5
+
+
 def test_srh_nonmonotone_pressure_takes_exact_path(core, oracle_mod):
     """Duplicate / out-of-order pressure levels: the kernel's EXACT path must reproduce
     DINTERP2DZ's top-down 'highest bracket wins' search literally."""

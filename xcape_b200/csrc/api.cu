@@ -192,7 +192,29 @@ int srh_device_t(const void* p, const void* t, const void* td, const void* u, co
   }
   a.ncol = ncol; a.ld = ld; a.nlev = nlev; a.depth = depth; a.aglh0 = aglh0;
   a.srh_rm = srh_rm; a.srh_lm = srh_lm; a.rm = rm; a.lm = lm; a.mean6 = mean6;
+  { int32_t* wl; int* wc; XC_CUDA(sc.alloc(&wl, (size_t)ncol)); XC_CUDA(sc.alloc(&wc, (size_t)1)); a.work_list = wl; a.work_count = wc; }
   return launch_srh(a, p_is_1d != 0, s);
+}
+
+// srh.srh signature: heights are given (float64 from stdheight in the reference)
+template <class T>
+int srh_heights_device_t(const void* u, const void* v, const void* aglh, const void* us, const void* vs, const void* aglhs,
+                         int64_t ncol, int nlev, int dtype, int layout, int64_t ld_in, double depth, const int32_t* start_3d,
+                         double* srh_rm, double* srh_lm, float* rm, float* lm, float* mean6, cudaStream_t s) {
+  Scratch sc(s);
+  SrhArgs<T> a{};
+  int rc;
+  const void* q;
+  int64_t ld = ncol, l2 = ncol;
+  if ((rc = canon3d_same(u, dtype, layout, ncol, nlev, ld_in, sc, &q, &ld, s))) return rc; a.u = (const T*)q;
+  if ((rc = canon3d_same(v, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.v = (const T*)q;
+  if ((rc = canon3d_same(aglh, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.aglh = (const T*)q;
+  a.us = (const T*)us; a.vs = (const T*)vs; a.aglhs = (const T*)aglhs;
+  a.start = start_3d;
+  a.ncol = ncol; a.ld = ld; a.nlev = nlev; a.depth = depth; a.aglh0 = 0.0;
+  a.srh_rm = srh_rm; a.srh_lm = srh_lm; a.rm = rm; a.lm = lm; a.mean6 = mean6;
+  { int32_t* wl; int* wc; XC_CUDA(sc.alloc(&wl, (size_t)ncol)); XC_CUDA(sc.alloc(&wc, (size_t)1)); a.work_list = wl; a.work_count = wc; }
+  return launch_srh(a, false, s);
 }
 
 template <class T>
@@ -513,6 +535,38 @@ int xcape_cuda_srh(const void* p, const void* t, const void* td, const void* u, 
                                  b.in1[2], b.in1[3], b.in1[4], n, n, start_3d ? (const int32_t*)b.in1[5] : nullptr,
                                  (double*)b.out[0], (double*)b.out[1], rm ? (float*)b.out[2] : nullptr,
                                  lm ? (float*)b.out[3] : nullptr, mean6 ? (float*)b.out[4] : nullptr, s);
+                    });
+}
+
+int xcape_cuda_srh_from_heights(const void* u, const void* v, const void* aglh, const void* us, const void* vs,
+                                const void* aglhs, int64_t ncol, int nlev, int dtype, int layout, int mem, double depth,
+                                const int32_t* start_3d, double* srh_rm, double* srh_lm, float* rm, float* lm,
+                                float* mean6, int device, void* stream) {
+  int rc = check_common(ncol, nlev, dtype, layout, mem);
+  if (rc) return rc;
+  if (ncol == 0) return XCAPE_OK;
+  if (!u || !v || !aglh || !us || !vs || !aglhs || !srh_rm || !srh_lm) return fail(XCAPE_ERR_ARG, "null pointer");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(XCAPE_ERR_NODEV, "cudaSetDevice failed");
+  auto dev = [&](const void* u_, const void* v_, const void* h_, const void* us_, const void* vs_, const void* hs_, int64_t n,
+                 const int32_t* st_, double* srm_, double* slm_, float* rm_, float* lm_, float* m6_, cudaStream_t s) {
+    if (dtype == XCAPE_F64)
+      return srh_heights_device_t<double>(u_, v_, h_, us_, vs_, hs_, n, nlev, dtype, layout, n, depth, st_, srm_, slm_, rm_, lm_, m6_, s);
+    return srh_heights_device_t<float>(u_, v_, h_, us_, vs_, hs_, n, nlev, dtype, layout, n, depth, st_, srm_, slm_, rm_, lm_, m6_, s);
+  };
+  if (mem == XCAPE_MEM_DEVICE)
+    return dev(u, v, aglh, us, vs, aglhs, ncol, start_3d, srh_rm, srh_lm, rm, lm, mean6, (cudaStream_t)stream);
+  const size_t es = esize(dtype);
+  std::vector<HostIn3> in3 = {{u}, {v}, {aglh}};
+  std::vector<HostIn1> in1 = {{us, es}, {vs, es}, {aglhs, es}};
+  if (start_3d) in1.push_back({start_3d, 4});
+  std::vector<HostOut> outs = {{srh_rm, 8, 0}, {srh_lm, 8, 0}, {rm, 8, 0}, {lm, 8, 0}, {mean6, 8, 0}};
+  return run_staged(ncol, nlev, layout, es, nullptr, in3, in1, outs,
+                    [&](Block& b, int64_t n, cudaStream_t s) {
+                      return dev(b.in3[0], b.in3[1], b.in3[2], b.in1[0], b.in1[1], b.in1[2], n,
+                                 start_3d ? (const int32_t*)b.in1[3] : nullptr, (double*)b.out[0], (double*)b.out[1],
+                                 rm ? (float*)b.out[2] : nullptr, lm ? (float*)b.out[3] : nullptr,
+                                 mean6 ? (float*)b.out[4] : nullptr, s);
                     });
 }
 

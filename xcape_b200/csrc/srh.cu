@@ -1,6 +1,8 @@
 // srh.cu — instantiations of the fused SRH kernel and the heights-only kernel.
 // Compiled with -fmad=false so that the binary64 height chain and the binary32 Bunkers
 // chain round operation by operation like the reference.
+#include <algorithm>
+
 #include "xc_common.cuh"
 #include "srh_kernel.cuh"
 #include "srh_launch.cuh"
@@ -11,8 +13,16 @@ template <class T>
 int launch_srh_t(const SrhArgs<T>& a, bool p1d, cudaStream_t s) {
   if (a.ncol <= 0) return XCAPE_OK;
   const unsigned blocks = (unsigned)((a.ncol + 127) / 128);
-  if (p1d) srh_kernel<T, true><<<blocks, 128, 0, s>>>(a);
-  else srh_kernel<T, false><<<blocks, 128, 0, s>>>(a);
+  if (a.ncol >= (int64_t)1 << 31) return fail(XCAPE_ERR_ARG, "srh: more than 2^31-1 columns per call");
+  XC_CUDA(cudaMemsetAsync(a.work_count, 0, sizeof(int), s));
+  if (a.aglh) srh_kernel<T, false, true><<<blocks, 128, 0, s>>>(a);
+  else if (p1d) srh_kernel<T, true, false><<<blocks, 128, 0, s>>>(a);
+  else srh_kernel<T, false, false><<<blocks, 128, 0, s>>>(a);
+  XC_LAUNCH_CHECK();
+  const unsigned eb = (unsigned)std::min<int64_t>(blocks, 148 * 4);   // grid-stride over the (usually empty) work list
+  if (a.aglh) srh_exact_kernel<T, false, true><<<eb, 128, 0, s>>>(a);
+  else if (p1d) srh_exact_kernel<T, true, false><<<eb, 128, 0, s>>>(a);
+  else srh_exact_kernel<T, false, false><<<eb, 128, 0, s>>>(a);
   XC_LAUNCH_CHECK();
   return XCAPE_OK;
 }

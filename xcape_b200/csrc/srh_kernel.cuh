@@ -38,6 +38,8 @@ struct SrhArgs {
   const T* __restrict__ tds;
   const T* __restrict__ us;
   const T* __restrict__ vs;
+  const T* __restrict__ aglh;   // heights given (srh.srh signature): level-major [nlev][ld]; else nullptr
+  const T* __restrict__ aglhs;  // [ncol] height of the surface level when aglh is given
   const int32_t* __restrict__ start;   // 1-based or nullptr
   int64_t ncol, ld;
   int nlev;
@@ -47,6 +49,8 @@ struct SrhArgs {
   float* __restrict__ rm;       // [2*ncol] or nullptr
   float* __restrict__ lm;
   float* __restrict__ mean6;
+  int32_t* __restrict__ work_list;   // [ncol] scratch: columns deferred to the EXACT kernel
+  int* __restrict__ work_count;      // zeroed by the launcher
 };
 
 // stdheight_2D_model_lev.f90:90-125 — binary64 arithmetic on single-precision literals
@@ -111,15 +115,25 @@ __device__ __forceinline__ double ld_p(const SrhArgs<T>& a, int64_t c, int lev) 
   return (double)(P1D ? __ldg(a.p + lev) : a.p[(int64_t)lev * a.ld + c]);
 }
 
-// Returns false when the column needs the EXACT path (pressure not strictly decreasing).
-template <class T, bool P1D, bool EXACT>
-__device__ bool srh_column(const SrhArgs<T>& a, int64_t c, int ks, SrhOut& o) {
+// Returns false when the column needs the EXACT path (pressure not strictly decreasing /
+// given heights not strictly increasing).  HG: heights are given (a.aglh, a.aglhs) instead of
+// being integrated from p, t, td — the reference's separate srh.srh call (srh.py:4).
+// The EXACT instantiation is kept out of line so that its 26 sample registers and second height
+// pass do not inflate the register count (and lower the occupancy) of the streaming path.
+template <class T, bool P1D, bool EXACT, bool HG>
+__device__ __forceinline__ bool srh_column(const SrhArgs<T>& a, int64_t c, int ks, SrhOut& o) {
   const int n3 = a.nlev - ks + 1;                 // 3-D levels used
-  const double Ps = (double)a.ps[c];
-  double Tvp = tvirt((double)a.ts[c], (double)a.tds[c], Ps);
-  double Hp = a.aglh0, Pp = Ps, lnPp = spec_log_d(Ps);
+  double Tvp = 0.0, Pp = 0.0, lnPp = 0.0, Hp;
+  if (HG) {
+    Hp = (double)a.aglhs[c];
+  } else {
+    const double Ps = (double)a.ps[c];
+    Tvp = tvirt((double)a.ts[c], (double)a.tds[c], Ps);
+    Hp = a.aglh0; Pp = Ps; lnPp = spec_log_d(Ps);
+  }
+  const double Hs = Hp;
   double up = (double)a.us[c], vp = (double)a.vs[c];
-  float upf = (float)a.us[c], vpf = (float)a.vs[c], zpf = (float)a.aglh0;
+  float upf = (float)a.us[c], vpf = (float)a.vs[c], zpf = (float)Hp;
 
   // Bunkers samples: index 0 = surface wind, 1..12 = 500 m .. 6000 m
   float su[EXACT ? 13 : 1], sv[EXACT ? 13 : 1];
@@ -135,16 +149,20 @@ __device__ bool srh_column(const SrhArgs<T>& a, int64_t c, int ks, SrhOut& o) {
   if (EXACT) {
     // DINTERP2DZ orientation test Z(1) > Z(NZ) needs the top height first (f90:211-216)
     double H = Hp, Tv0 = Tvp, lnP0 = lnPp;
-    for (int i = 0; i < n3; ++i) {
-      const int lev = ks - 1 + i;
-      const int64_t off = (int64_t)lev * a.ld + c;
-      const double P = ld_p<T, P1D>(a, c, lev);
-      const double Tv = tvirt((double)a.t[off], (double)a.td[off], P);
-      const double lnP = spec_log_d(P);
-      H = hyps_step(H, Tv, Tv0, lnP, lnP0);
-      Tv0 = Tv; lnP0 = lnP;
+    if (HG) {
+      H = (double)a.aglh[(int64_t)(ks - 1 + n3 - 1) * a.ld + c];
+    } else {
+      for (int i = 0; i < n3; ++i) {
+        const int lev = ks - 1 + i;
+        const int64_t off = (int64_t)lev * a.ld + c;
+        const double P = ld_p<T, P1D>(a, c, lev);
+        const double Tv = tvirt((double)a.t[off], (double)a.td[off], P);
+        const double lnP = spec_log_d(P);
+        H = hyps_step(H, Tv, Tv0, lnP, lnP0);
+        Tv0 = Tv; lnP0 = lnP;
+      }
     }
-    descending = ((float)a.aglh0 > (float)H);
+    descending = ((float)Hs > (float)H);
   }
 
   bool found_top = false;
@@ -154,12 +172,18 @@ __device__ bool srh_column(const SrhArgs<T>& a, int64_t c, int ks, SrhOut& o) {
   for (; i < n3; ++i) {
     const int lev = ks - 1 + i;
     const int64_t off = (int64_t)lev * a.ld + c;
-    const double P = ld_p<T, P1D>(a, c, lev);
-    if (!(P < Pp)) mono = false;
     const T uin = a.u[off], vin = a.v[off];
-    const double Tv = tvirt((double)a.t[off], (double)a.td[off], P);
-    const double lnP = spec_log_d(P);
-    const double H = hyps_step(Hp, Tv, Tvp, lnP, lnPp);        // stdheight_2D_model_lev.f90:143,152
+    double P = 0.0, Tv = 0.0, lnP = 0.0, H;
+    if (HG) {
+      H = (double)a.aglh[off];
+      if (!(H > Hp)) mono = false;
+    } else {
+      P = ld_p<T, P1D>(a, c, lev);
+      if (!(P < Pp)) mono = false;
+      Tv = tvirt((double)a.t[off], (double)a.td[off], P);
+      lnP = spec_log_d(P);
+      H = hyps_step(Hp, Tv, Tvp, lnP, lnPp);                    // stdheight_2D_model_lev.f90:143,152
+    }
     const double uk = (double)uin, vk = (double)vin;
     const float ukf = (float)uin, vkf = (float)vin, zkf = (float)H;
 
@@ -215,9 +239,15 @@ __device__ bool srh_column(const SrhArgs<T>& a, int64_t c, int ks, SrhOut& o) {
   }
   if (!EXACT) {
     for (; i < n3; ++i) {                          // monotonicity check only: loads, no math
-      const double P = ld_p<T, P1D>(a, c, ks - 1 + i);
-      if (!(P < Pp)) mono = false;
-      Pp = P;
+      if (HG) {
+        const double H = (double)a.aglh[(int64_t)(ks - 1 + i) * a.ld + c];
+        if (!(H > Hp)) mono = false;
+        Hp = H;
+      } else {
+        const double P = ld_p<T, P1D>(a, c, ks - 1 + i);
+        if (!(P < Pp)) mono = false;
+        Pp = P;
+      }
     }
     if (!mono) return false;
     for (; j < 13; ++j) {                          // column top below the sample height: VMSG enters the mean
@@ -240,18 +270,39 @@ __device__ bool srh_column(const SrhArgs<T>& a, int64_t c, int ks, SrhOut& o) {
   return true;
 }
 
-template <class T, bool P1D>
+template <class T>
+__device__ __forceinline__ void srh_store(const SrhArgs<T>& a, int64_t c, const SrhOut& o) {
+  a.srh_rm[c] = o.srm; a.srh_lm[c] = o.slm;
+  if (a.rm) { a.rm[2 * c] = o.rmu; a.rm[2 * c + 1] = o.rmv; }
+  if (a.lm) { a.lm[2 * c] = o.lmu; a.lm[2 * c + 1] = o.lmv; }
+  if (a.mean6) { a.mean6[2 * c] = o.m6u; a.mean6[2 * c + 1] = o.m6v; }
+}
+
+// Streaming pass.  Columns that need the literal DINTERP2DZ search (non-monotone pressure /
+// heights) are appended to a work list and left to srh_exact_kernel, so that the EXACT code's
+// registers (13 + 13 samples, second height pass) never limit this kernel's occupancy.
+template <class T, bool P1D, bool HG>
 __global__ void __launch_bounds__(128) srh_kernel(const SrhArgs<T> a) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.ncol) return;
   int ks = a.start ? a.start[c] : 1;
   ks = ks < 1 ? 1 : (ks > a.nlev ? a.nlev : ks);
   SrhOut o;
-  if (!srh_column<T, P1D, false>(a, c, ks, o)) srh_column<T, P1D, true>(a, c, ks, o);
-  a.srh_rm[c] = o.srm; a.srh_lm[c] = o.slm;
-  if (a.rm) { a.rm[2 * c] = o.rmu; a.rm[2 * c + 1] = o.rmv; }
-  if (a.lm) { a.lm[2 * c] = o.lmu; a.lm[2 * c + 1] = o.lmv; }
-  if (a.mean6) { a.mean6[2 * c] = o.m6u; a.mean6[2 * c + 1] = o.m6v; }
+  if (srh_column<T, P1D, false, HG>(a, c, ks, o)) srh_store(a, c, o);
+  else a.work_list[atomicAdd(a.work_count, 1)] = (int32_t)c;
+}
+
+template <class T, bool P1D, bool HG>
+__global__ void __launch_bounds__(128) srh_exact_kernel(const SrhArgs<T> a) {
+  const int n = *a.work_count;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int64_t c = a.work_list[k];
+    int ks = a.start ? a.start[c] : 1;
+    ks = ks < 1 ? 1 : (ks > a.nlev ? a.nlev : ks);
+    SrhOut o;
+    srh_column<T, P1D, true, HG>(a, c, ks, o);
+    srh_store(a, c, o);
+  }
 }
 
 // Heights only: loop_stdheight_ml / loop_stdheight_pl1d.  Output strides let the caller pick

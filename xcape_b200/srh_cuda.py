@@ -3,7 +3,9 @@
 The reference computes SRH with three f2py calls that exchange two full float64 height
 arrays (core.py:516-535 -> stdheight.py:20-36 -> srh.py:41-61).  ``srh_fused`` makes ONE call
 to ``xcape_cuda_srh`` (include/xcape_b200.h), which produces heights, Bunkers storm motion
-and both helicity integrals in a single pass over the column.
+and both helicity integrals in a single pass over the column.  ``srh`` keeps the reference's
+two-call form (same signature as ``xcape.srh.srh``, heights supplied by the caller, e.g. from
+``stdheight_cuda.stdheight``) through ``xcape_cuda_srh_from_heights``.
 """
 import ctypes as C
 
@@ -96,5 +98,42 @@ def srh_fused(p_2d, t_2d, td_2d, u_2d, v_2d, p_s, t_s, td_s, u_s, v_s, flag_1d, 
     if not want_all:
         return srm, slm
     # hand back the reference's (2, ngrid) view (srh.py:42-43: rm_sup[0, :] is the u component)
+    tr = (lambda a: a.t()) if A.is_cuda(ref) else (lambda a: a.T)
+    return srm, slm, tr(rm), tr(lm), tr(m6)
+
+
+def srh(u_2d, v_2d, aglh_2d, u_s, v_s, aglh_s, pres_lev_pos, depth, type_grid, output, *, device=0, stream=None):
+    """Same arguments and returns as ``xcape.srh.srh`` (srh.py:4-66): winds and heights ``(nlev,
+    ngrid)``, surface values ``(ngrid,)``; ``pres_lev_pos`` (1-based first level used) only matters
+    for ``type_grid == 2``.  Replaces ``bunkers_loop_*`` + ``loop_sreh_*``."""
+    L = _lib.lib()
+    nlev, ngrid = u_2d.shape
+    if type_grid not in (1, 2):
+        raise ValueError('type_grid must be 1 (model levels) or 2 (pressure levels)')
+    f3, f1, _, dt, layout, mem, ref = A.prepare_fields([u_2d, v_2d, aglh_2d], [u_s, v_s, aglh_s])
+    if any(tuple(a.shape) != (nlev, ngrid) for a in f3) or any(a.shape[0] != ngrid for a in f1):
+        raise ValueError('Input arrays must have the same shape.')
+    u_, v_, h_ = f3
+    us_, vs_, hs_ = f1
+    start = None
+    if type_grid == 2 and pres_lev_pos is not None:
+        if A.is_cuda(ref):
+            import torch
+            start = torch.as_tensor(pres_lev_pos, device=ref.device).to(torch.int32).expand(ngrid).contiguous()
+        else:
+            start = np.ascontiguousarray(np.broadcast_to(np.asarray(pres_lev_pos), (ngrid,)), dtype=np.int32)
+    want_all = (output != 1)
+    srm = A.empty_like_host_or_device(ref, (ngrid,), 'float64')
+    slm = A.empty_like_host_or_device(ref, (ngrid,), 'float64')
+    rm = A.empty_like_host_or_device(ref, (ngrid, 2), 'float32') if want_all else None
+    lm = A.empty_like_host_or_device(ref, (ngrid, 2), 'float32') if want_all else None
+    m6 = A.empty_like_host_or_device(ref, (ngrid, 2), 'float32') if want_all else None
+    rc = L.xcape_cuda_srh_from_heights(A.ptr(u_), A.ptr(v_), A.ptr(h_), A.ptr(us_), A.ptr(vs_), A.ptr(hs_),
+                                       C.c_int64(ngrid), nlev, dt, layout, mem, C.c_double(float(depth)), A.ptr(start),
+                                       A.ptr(srm), A.ptr(slm), A.ptr(rm), A.ptr(lm), A.ptr(m6),
+                                       A.device_of(ref, device), A.stream_of(ref, stream))
+    _lib.check(rc)
+    if not want_all:
+        return srm, slm
     tr = (lambda a: a.t()) if A.is_cuda(ref) else (lambda a: a.T)
     return srm, slm, tr(rm), tr(lm), tr(m6)
