@@ -407,3 +407,28 @@ def test_fast_mode_goldens(core, soundings, era5pl):
         close_decimal(r[1], era5pl['surf_' + gi], 0)
     with pytest.raises(ValueError):
         core.calc_cape(*era_cape_args(era5pl), vertical_lev='pressure', method='cuda', precision='sloppy')
+
+
+# ------------------------------------------------------------------ several GPUs in one process
+def test_devices_kwarg_shards_columns_over_gpus(core):
+    """`devices=[0, 1, ...]`: contiguous 128-aligned column blocks, one host thread per GPU, no
+    collective; results identical to the single-GPU call.  Skipped on a one-GPU box."""
+    from xcape_b200 import _lib
+    from xcape_b200.synthetic import make_soundings
+    n = min(_lib.device_count(), 4)
+    if n < 2:
+        pytest.skip('needs >= 2 GPUs')
+    d = make_soundings('C2', cols=(0, 300_000 + 77))
+    args = (d['p'], d['t'], d['td'], d['ps'], d['ts'], d['tds'])
+    kw = dict(source='most-unstable', pinc=500., vertical_lev='pressure', method='cuda')
+    one = core.calc_cape(*args, **kw)
+    many = core.calc_cape(*args, devices=list(range(n)), **kw)
+    assert_bitexact(many, one, f'devices=0..{n - 1}')
+    d3 = make_soundings('C3', cols=(0, 100_000 + 5))
+    sargs = tuple(d3[k] for k in ('p', 't', 'td', 'u', 'v', 'ps', 'ts', 'tds', 'us', 'vs'))
+    s1 = core.calc_srh(*sargs, vertical_lev='sigma', output_var='all', method='cuda')
+    sn = core.calc_srh(*sargs, vertical_lev='sigma', output_var='all', method='cuda', devices=list(range(n)))
+    for a, b in zip(sn, s1):
+        assert np.array_equal(a, b)
+    other = core.calc_cape(*args, device=n - 1, **kw)          # explicit non-default device
+    assert_bitexact(other, one, f'device={n - 1}')
