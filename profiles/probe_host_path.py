@@ -23,7 +23,7 @@ if len(sys.argv) > 1 and sys.argv[1] == 'child':
     t0 = time.perf_counter()
     for _ in range(3): g()
     dp = (time.perf_counter() - t0) / 3
-    print(f"chunk={os.environ.get('XCAPE_B200_CHUNK_COLS')} first={os.environ.get('XCAPE_B200_FIRST_CHUNK_COLS')} streams={os.environ.get('XCAPE_B200_STREAMS')}: pinned {dt*1e3:.2f} ms/field ({d['t'].shape[0]/dt/1e6:.1f} Mcol/s)  pageable {dp*1e3:.2f} ms/field")
+    print(f"chunk={os.environ.get('XCAPE_B200_CHUNK_COLS')} first={os.environ.get('XCAPE_B200_FIRST_CHUNK_COLS')} streams={os.environ.get('XCAPE_B200_STREAMS')} copy_threads={os.environ.get('XCAPE_B200_COPY_THREADS')}: pinned {dt*1e3:.2f} ms/field ({d['t'].shape[0]/dt/1e6:.1f} Mcol/s)  pageable {dp*1e3:.2f} ms/field")
     sys.exit(0)
 
 x = torch.empty(320 * 1024 * 1024 // 4, dtype=torch.float32).pin_memory()
@@ -38,6 +38,6 @@ for _ in range(5): x.copy_(y, non_blocking=True)
 torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
 print(f'D2H pinned 320 MiB: {dt*1e3:.2f} ms  ({x.numel()*4/dt/1e9:.1f} GB/s)')
 del x, y
-for chunk, first, streams in ((524288, 32768, 4), (524288, 65536, 4), (262144, 32768, 4), (1048576, 32768, 4), (524288, 16384, 4), (131072, 131072, 4), (524288, 32768, 3)):
-    env = dict(os.environ, XCAPE_B200_CHUNK_COLS=str(chunk), XCAPE_B200_FIRST_CHUNK_COLS=str(first), XCAPE_B200_STREAMS=str(streams))
+for chunk, first, streams, thr in ((262144, 32768, 4, 8), (262144, 32768, 4, 4), (262144, 32768, 4, 2), (262144, 32768, 4, 16), (131072, 32768, 4, 8), (524288, 65536, 4, 8)):
+    env = dict(os.environ, XCAPE_B200_CHUNK_COLS=str(chunk), XCAPE_B200_FIRST_CHUNK_COLS=str(first), XCAPE_B200_STREAMS=str(streams), XCAPE_B200_COPY_THREADS=str(thr))
     print(subprocess.run([sys.executable, __file__, 'child'], env=env, capture_output=True, text=True).stdout.strip())

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "xc_common.cuh"
@@ -311,6 +312,29 @@ struct PinnedCache {
 };
 PinnedCache g_pinned;
 
+// Multi-threaded host copy into a pinned staging buffer (pageable caller memory would otherwise go
+// through the driver's single bounce buffer at ~12 GB/s and block the enqueuing thread).
+void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+  static const int nthr = (int)env_i64("XCAPE_B200_COPY_THREADS", std::min<int64_t>(8, std::max<int64_t>(1, std::thread::hardware_concurrency() / 2)), 1, 64);
+  if (bytes < ((size_t)4 << 20) || nthr == 1) { memcpy(dst, src, bytes); return; }
+  std::vector<std::thread> th;
+  const size_t part = ((bytes / nthr) + 4095) & ~(size_t)4095;
+  for (int t = 0; t < nthr; ++t) {
+    const size_t a = (size_t)t * part;
+    if (a >= bytes) break;
+    const size_t n = std::min(part, bytes - a);
+    th.emplace_back([=] { memcpy((char*)dst + a, (const char*)src + a, n); });
+  }
+  for (auto& x : th) x.join();
+}
+
+// columns [c0, c0+n) of a 3-D host field -> dense block of the same layout in `dst` (host)
+void stage_field(void* dst, const void* src, int layout, int64_t ncol, int nlev, int64_t c0, int64_t n, size_t es) {
+  if (layout == XCAPE_LEVEL_LAST) { parallel_memcpy(dst, (const char*)src + (size_t)c0 * nlev * es, (size_t)n * nlev * es); return; }
+  for (int k = 0; k < nlev; ++k)
+    memcpy((char*)dst + (size_t)k * n * es, (const char*)src + ((size_t)k * ncol + c0) * es, (size_t)n * es);
+}
+
 bool is_pageable_host(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
@@ -334,6 +358,11 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
   Block b[kMaxStreams];
   struct Pending { bool on = false; int64_t c0 = 0, n = 0; } pend[kMaxStreams];
   std::vector<void*> stage[kMaxStreams];          // pinned staging per output (nullptr = direct copy)
+  std::vector<void*> stage3[kMaxStreams], stage1[kMaxStreams];   // pinned staging per pageable input
+  std::vector<char> in3_pageable(in3.size(), 0), in1_pageable(in1.size(), 0);
+  const bool stage_inputs = env_i64("XCAPE_B200_STAGE_PAGEABLE", 1, 0, 1) != 0;
+  for (size_t k = 0; k < in3.size(); ++k) in3_pageable[k] = stage_inputs && is_pageable_host(in3[k].host);
+  for (size_t k = 0; k < in1.size(); ++k) in1_pageable[k] = stage_inputs && is_pageable_host(in1[k].host);
   std::vector<char> staged(outs.size(), 0);
   for (size_t k = 0; k < outs.size(); ++k)
     staged[k] = (outs[k].host && !outs[k].is3d && is_pageable_host(outs[k].host)) ? 1 : 0;
@@ -355,8 +384,18 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
     for (int i = 0; i < nstream; ++i) {
       XC_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
       XC_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-      for (size_t k = 0; k < in3.size(); ++k) { void* q; XC_CUDA(pool_alloc(&q, (size_t)chunk * nlev * es, st[i])); b[i].in3.push_back(q); }
-      for (size_t k = 0; k < in1.size(); ++k) { void* q; XC_CUDA(pool_alloc(&q, (size_t)chunk * in1[k].es, st[i])); b[i].in1.push_back(q); }
+      for (size_t k = 0; k < in3.size(); ++k) {
+        void* q; XC_CUDA(pool_alloc(&q, (size_t)chunk * nlev * es, st[i])); b[i].in3.push_back(q);
+        void* h = nullptr;
+        if (in3_pageable[k] && !(h = g_pinned.acquire((size_t)chunk * nlev * es))) return fail(XCAPE_ERR_CUDA, "cudaHostAlloc failed (input staging)");
+        stage3[i].push_back(h);
+      }
+      for (size_t k = 0; k < in1.size(); ++k) {
+        void* q; XC_CUDA(pool_alloc(&q, (size_t)chunk * in1[k].es, st[i])); b[i].in1.push_back(q);
+        void* h = nullptr;
+        if (in1_pageable[k] && !(h = g_pinned.acquire((size_t)chunk * in1[k].es))) return fail(XCAPE_ERR_CUDA, "cudaHostAlloc failed (input staging)");
+        stage1[i].push_back(h);
+      }
       for (size_t k = 0; k < outs.size(); ++k) {
         void* q; XC_CUDA(pool_alloc(&q, (size_t)chunk * (outs[k].is3d ? (size_t)nlev * 8 : outs[k].bytes_per_col), st[i]));
         b[i].out.push_back(q);
@@ -381,9 +420,19 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
       cudaStream_t s = st[i];
       int r = drain(i);                            // slot reuse: its previous block must have left
       if (r) return r;
-      for (size_t k = 0; k < in3.size(); ++k) XC_CUDA(h2d_field(b[i].in3[k], in3[k].host, layout, ncol, nlev, c0, n, es, s));
-      for (size_t k = 0; k < in1.size(); ++k)
-        XC_CUDA(cudaMemcpyAsync(b[i].in1[k], (const char*)in1[k].host + (size_t)c0 * in1[k].es, (size_t)n * in1[k].es, cudaMemcpyHostToDevice, s));
+      for (size_t k = 0; k < in3.size(); ++k) {
+        if (stage3[i][k]) {        // pageable: host threads fill the slot's pinned buffer, then a true async H2D
+          stage_field(stage3[i][k], in3[k].host, layout, ncol, nlev, c0, n, es);
+          XC_CUDA(cudaMemcpyAsync(b[i].in3[k], stage3[i][k], (size_t)n * nlev * es, cudaMemcpyHostToDevice, s));
+        } else {
+          XC_CUDA(h2d_field(b[i].in3[k], in3[k].host, layout, ncol, nlev, c0, n, es, s));
+        }
+      }
+      for (size_t k = 0; k < in1.size(); ++k) {
+        const void* src = (const char*)in1[k].host + (size_t)c0 * in1[k].es;
+        if (stage1[i][k]) { memcpy(stage1[i][k], src, (size_t)n * in1[k].es); src = stage1[i][k]; }
+        XC_CUDA(cudaMemcpyAsync(b[i].in1[k], src, (size_t)n * in1[k].es, cudaMemcpyHostToDevice, s));
+      }
       if ((r = launch(b[i], n, s))) return r;
       for (size_t k = 0; k < outs.size(); ++k) {
         if (!outs[k].host) continue;
@@ -418,6 +467,8 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
     }
     if (done[i]) cudaEventDestroy(done[i]);
     for (void* h : stage[i]) if (h) g_pinned.release(h);
+    for (void* h : stage3[i]) if (h) g_pinned.release(h);
+    for (void* h : stage1[i]) if (h) g_pinned.release(h);
   }
   if (rc) { cudaGetLastError(); g_last_error = keep; }
   if (trace) fprintf(stderr, "[xcape_b200] run_staged ncol=%lld blocks=%d streams=%d: body %.3f ms, teardown %.3f ms\n",
