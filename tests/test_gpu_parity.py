@@ -432,3 +432,22 @@ def test_devices_kwarg_shards_columns_over_gpus(core):
         assert np.array_equal(a, b)
     other = core.calc_cape(*args, device=n - 1, **kw)          # explicit non-default device
     assert_bitexact(other, one, f'device={n - 1}')
+
+
+@pytest.mark.parametrize('adiabat', ADIABATS)
+@pytest.mark.parametrize('source', ['surface', 'most-unstable'])
+def test_fast_mode_all_adiabats(core, oracle_mod, adiabat, source):
+    """precision='fast' for every adiabat (ice branches included) on 20 000 HRRR-shape columns:
+    tolerance-level parity against the reference arithmetic (oracle LIBM), MU level exact."""
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C3', cols=(500_000, 520_000))
+    args = (d['p'], d['t'], d['td'], d['ps'], d['ts'], d['tds'])
+    kw = dict(source=source, adiabat=adiabat, pinc=500., vertical_lev='sigma')
+    fast = core.calc_cape(*args, method='cuda', precision='fast', **kw)
+    ref, cnt = oracle_mod.calc_cape_ref(*args, tmode=oracle_mod.LIBM, nthreads=8, counters=True, **kw)
+    ok = (tol_ok(fast[0], ref[0]) & tol_ok(fast[1], ref[1])) | (cnt['status'] == 2)
+    print(f'{adiabat} {source}: outside tol {(~ok).sum()}/{ok.size}, max|dCAPE| {np.abs(fast[0] - ref[0])[ok].max():.3f}, '
+          f'mean {np.abs(fast[0] - ref[0]).mean():.4f} J/kg')
+    assert (~ok).sum() <= 2
+    if source == 'most-unstable':
+        assert np.array_equal(fast[2], ref[2]) or (fast[2] != ref[2]).mean() < 1e-3
