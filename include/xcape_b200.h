@@ -48,7 +48,13 @@ enum { XCAPE_FAITHFUL = 0,
  * moist fixed-point body runs on the FP32 pipe with FMAs, a ~1-ulp expf and MUFU reciprocals.
  * CAPE / CIN then agree with the reference within max(1 J/kg, 1e-4 relative) except on
  * ill-conditioned columns (non-convergence limit cycles, CIN sign flips). */
-       XCAPE_FAST = 1 };
+       XCAPE_FAST = 1,
+/* XCAPE_FAST additionally replaces the reference's damped fixed-point iteration of a sub-step
+ * (x += 0.3 g, ~10 passes) by a safeguarded secant solve of the same equation with the same stopping
+ * rule (3-5 passes) and advances the Exner function incrementally between level anchors.
+ * XCAPE_FAST_RELAXED keeps the reference's iteration (identical pass counts and non-convergence
+ * behaviour) and only uses the fast arithmetic. */
+       XCAPE_FAST_RELAXED = 2 };
 /* per-column status word (optional output) */
 enum { XCAPE_ST_OK = 0, XCAPE_ST_SKIPPED = 1 /* ts <= 0 degC gate, f90:77 */,
        XCAPE_ST_NONCONVERGED = 2 /* > 100 moist iterations, f90:464-474: cape = cin = 0 */ };

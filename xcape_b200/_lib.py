@@ -13,8 +13,8 @@ LIB_PATH = os.path.join(_HERE, 'libxcape_b200.so')
 F32, F64 = 0, 1
 LEVEL_LAST, LEVEL_MAJOR = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
-FAITHFUL, FAST = 0, 1
-PRECISION = {'faithful': FAITHFUL, 'fast': FAST}
+FAITHFUL, FAST, FAST_RELAXED = 0, 1, 2
+PRECISION = {'faithful': FAITHFUL, 'fast': FAST, 'fast-relaxed': FAST_RELAXED}
 OK, ERR_ARG, ERR_CUDA, ERR_NODEV = 0, 1, 2, 3
 
 # every symbol include/xcape_b200.h declares (tests check the library exports all of them)

@@ -11,17 +11,24 @@ namespace xc {
 
 struct MathSpec {
   static constexpr bool kFastBody = false;
+  static constexpr bool kSecant = false;
   static __device__ __forceinline__ float exp(float x) { return spec_expf(x); }
   static __device__ __forceinline__ float exp_small(float x) { return spec_expf_small(x); }
   static __device__ __forceinline__ float log(float x) { return spec_logf(x); }
   static __device__ __forceinline__ float pow(float x, float y) { return spec_powf(x, y); }
 };
 
-#ifdef XC_FAST_TU
-// Same SPEC prep arithmetic (so source selection / MU index stay bit-exact), FAST moist body.
-struct MathFast : MathSpec { static constexpr bool kFastBody = true; };
+#if defined(XC_FAST_TU)
+// Same SPEC prep arithmetic (so source selection / MU index stay bit-exact), FAST moist body,
+// secant-accelerated sub-step solve.
+struct MathFast : MathSpec { static constexpr bool kFastBody = true; static constexpr bool kSecant = true; };
 using MathPolicy = MathFast;
 #define XC_LAUNCH_NAME launch_cape_fast
+#elif defined(XC_FAST_RELAXED_TU)
+// FAST moist body, but the reference's own damped iteration (same pass counts as the reference).
+struct MathFastRelaxed : MathSpec { static constexpr bool kFastBody = true; };
+using MathPolicy = MathFastRelaxed;
+#define XC_LAUNCH_NAME launch_cape_fast_relaxed
 #else
 using MathPolicy = MathSpec;
 #define XC_LAUNCH_NAME launch_cape_faithful
