@@ -381,18 +381,22 @@ def test_fast_mode_within_stated_tolerance(core, oracle_mod, cfg, vertical_lev, 
     ref, cnt = oracle_mod.calc_cape_ref(*args, tmode=oracle_mod.LIBM, nthreads=8, counters=True, **kw)
     per = oracle_mod.calc_cape_ref(*args, tmode=oracle_mod.LIBM, nthreads=8, contract=True, **kw)
     ill = ~(tol_ok(per[0], ref[0]) & tol_ok(per[1], ref[1])) | (cnt['status'] == 2)
-    ok = tol_ok(fast[0], ref[0]) & tol_ok(fast[1], ref[1])
-    n = ok.size
-    bad_well = (~ok & ~ill).sum()
-    print(f'{cfg} {source} {precision}: outside tol {(~ok).sum()}/{n}, ill-conditioned {ill.sum()}, outside & well-conditioned {bad_well}; '
-          f'max|dCAPE| well-cond {np.abs(fast[0] - ref[0])[~ill].max():.3f} J/kg, mean {np.abs(fast[0] - ref[0]).mean():.4f}')
-    assert bad_well <= max(2, n // 20000), bad_well
-    assert (~ok).mean() < 1e-3
+    cape_ok, cin_ok = tol_ok(fast[0], ref[0]), tol_ok(fast[1], ref[1])
+    n = cape_ok.size
+    print(f'{cfg} {source} {precision}: CAPE outside tol {(~cape_ok).sum()}/{n}, CIN outside tol {(~cin_ok).sum()}/{n} '
+          f'(oracle-ill-conditioned {ill.sum()}); max|dCAPE| {np.abs(fast[0] - ref[0])[~ill].max():.3f} J/kg, '
+          f'mean {np.abs(fast[0] - ref[0]).mean():.4f}')
+    # CAPE: inside the stated tolerance on every column the reference itself computes stably.
+    assert (~cape_ok & ~ill).sum() == 0
+    # CIN: the reference credits negative area only when positive area is (re)entered (f90:509-523), so
+    # CIN jumps by tens of J/kg when a near-zero buoyancy changes sign — typically on columns with
+    # CAPE < 1 J/kg.  Those sign flips are the only disagreements and stay below 1e-4 of the columns.
+    assert (~cin_ok).mean() < 1e-4, (~cin_ok).sum()
     if source == 'most-unstable':
         assert np.array_equal(fast[2], exact[2])                   # MU level: same prep arithmetic, bit-exact
         assert (fast[3] != exact[3]).mean() < 1e-3                 # last level reached can differ on a sign flip
     # the fast body must not be further from the reference than the faithful one by more than a fraction of the tolerance
-    assert np.abs(fast[0] - ref[0])[~ill].mean() < 0.1
+    assert np.abs(fast[0] - ref[0])[~ill].mean() < 0.1 and np.abs(fast[0] - ref[0])[~ill].max() < 0.5
 
 
 def test_fast_mode_goldens(core, soundings, era5pl):
@@ -451,9 +455,46 @@ def test_fast_mode_all_adiabats(core, oracle_mod, adiabat, source, precision):
     kw = dict(source=source, adiabat=adiabat, pinc=500., vertical_lev='sigma')
     fast = core.calc_cape(*args, method='cuda', precision=precision, **kw)
     ref, cnt = oracle_mod.calc_cape_ref(*args, tmode=oracle_mod.LIBM, nthreads=8, counters=True, **kw)
-    ok = (tol_ok(fast[0], ref[0]) & tol_ok(fast[1], ref[1])) | (cnt['status'] == 2)
-    print(f'{adiabat} {source} {precision}: outside tol {(~ok).sum()}/{ok.size}, max|dCAPE| {np.abs(fast[0] - ref[0])[ok].max():.3f}, '
-          f'mean {np.abs(fast[0] - ref[0]).mean():.4f} J/kg')
-    assert (~ok).sum() <= 2
+    conv = cnt['status'] != 2
+    cape_ok, cin_ok = tol_ok(fast[0], ref[0]) | ~conv, tol_ok(fast[1], ref[1]) | ~conv
+    print(f'{adiabat} {source} {precision}: CAPE outside tol {(~cape_ok).sum()}, CIN outside tol {(~cin_ok).sum()} of {conv.size}; '
+          f'max|dCAPE| {np.abs(fast[0] - ref[0])[conv].max():.3f}, mean {np.abs(fast[0] - ref[0]).mean():.4f} J/kg')
+    assert cape_ok.all()
+    assert (~cin_ok).sum() <= 3          # CIN-credit sign flips (see test_fast_mode_within_stated_tolerance)
     if source == 'most-unstable':
         assert np.array_equal(fast[2], ref[2]) or (fast[2] != ref[2]).mean() < 1e-3
+
+
+@pytest.mark.parametrize('precision', ['fast', 'fast-relaxed'])
+def test_fast_mode_on_edge_columns(core, oracle_mod, precision):
+    """The edge set of test_gate_nonconvergence_and_high_surface in the fast modes: gates and the
+    high-surface MU rule are exact (shared prep code); outputs are finite; where the reference
+    converges the tolerance holds.  Where the reference gives up after 100 passes (status 2 ->
+    cape = cin = 0) 'fast-relaxed' gives up too (same iteration); 'fast' (secant) may converge and
+    then reports the converged CAPE with status 0 — the one documented behavioural difference."""
+    from xcape_b200.cape_cuda import cape as cape_cuda
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C1', cols=(0, 512))
+    p, t, td, ps, ts, tds = (d[k].copy() for k in ('p', 't', 'td', 'ps', 'ts', 'tds'))
+    ts[0] = 0.0; ts[1] = -3.0; ts[2] = np.nan
+    ts[8:72] = np.linspace(33.0, 38.0, 64); tds[8:72] = ts[8:72] - np.linspace(0.2, 2.0, 64)
+    t[8:72, 0] = ts[8:72] - 0.5; td[8:72, 0] = tds[8:72] - 0.5
+    ps[100:110] = 480.0; p[100:110] = (480.0 * np.linspace(0.99, 0.02, 50)).astype(np.float32)
+    for source, src in (('surface', 1), ('most-unstable', 2), ('mixed-layer', 3)):
+        got = cape_cuda(p.T, t.T, td.T, ps, ts, tds, 0, 1, src, 500., 1, 500., 1, precision=precision, return_counters=True)
+        ref, cnt = oracle_mod.calc_cape_ref(p, t, td, ps, ts, tds, source=source, pinc=500., vertical_lev='sigma',
+                                            tmode=oracle_mod.LIBM, counters=True)
+        assert np.isfinite(got[0]).all() and np.isfinite(got[1]).all()
+        assert set(np.unique(got[4])) <= {0, 1, 2} and (got[5] <= 101 * 400).all()
+        assert (got[4][:3] == 1).all() and (got[0][:3] == 0).all()
+        conv = cnt['status'] == 0
+        assert tol_ok(got[0], ref[0])[conv].all()
+        assert (~tol_ok(got[1], ref[1])[conv]).sum() <= 1
+        if source == 'most-unstable':
+            assert np.array_equal(got[2], ref[2]) and (got[2][100:110] == -999999).all()
+        if precision == 'fast-relaxed':
+            assert ((got[4] == 2) == (cnt['status'] == 2)).mean() > 0.95      # limit cycles are arithmetic-sensitive
+        else:
+            gave_up = cnt['status'] == 2
+            print(f'{source}: reference gives up on {gave_up.sum()} columns; secant solve converges on '
+                  f'{(got[4][gave_up] == 0).sum()} of them')
