@@ -487,13 +487,17 @@ def test_fast_mode_on_edge_columns(core, oracle_mod, precision):
         assert np.isfinite(got[0]).all() and np.isfinite(got[1]).all()
         assert set(np.unique(got[4])) <= {0, 1, 2} and (got[5] <= 101 * 400).all()
         assert (got[4][:3] == 1).all() and (got[0][:3] == 0).all()
-        conv = cnt['status'] == 0
+        # compare where both converged: whether an extreme parcel's damped iteration falls into a limit
+        # cycle depends on last-bit arithmetic, so 'fast-relaxed' may give up on a few columns
+        # the reference (just) converges on, and vice versa
+        conv = (cnt['status'] == 0) & (got[4] == 0)
         assert tol_ok(got[0], ref[0])[conv].all()
         assert (~tol_ok(got[1], ref[1])[conv]).sum() <= 1
+        assert ((cnt['status'] == 0) & (got[4] == 2)).sum() <= (8 if precision == 'fast-relaxed' else 0)
         if source == 'most-unstable':
             assert np.array_equal(got[2], ref[2]) and (got[2][100:110] == -999999).all()
         if precision == 'fast-relaxed':
-            assert ((got[4] == 2) == (cnt['status'] == 2)).mean() > 0.95      # limit cycles are arithmetic-sensitive
+            assert ((got[4] == 2) == (cnt['status'] == 2)).mean() > 0.95
         else:
             gave_up = cnt['status'] == 2
             print(f'{source}: reference gives up on {gave_up.sum()} columns; secant solve converges on '
