@@ -23,7 +23,8 @@ forwards to an installed reference ``xcape`` if there is one); ``calc_srh`` gain
 its code does not, core.py:229); inputs may be torch CUDA tensors (results are then CUDA tensors);
 ``lev_axis=0`` accepts level-major ``[nlev, ...]`` arrays (the on-disk order of ERA5 / HRRR) with
 zero relayout; ``device=`` / ``devices=[...]`` pick the GPU(s); ``calc_cape(precision='fast')`` trades
-bit-exactness of CAPE/CIN for about twice the speed (tolerance-level parity, MU level still exact).
+bit-exactness of CAPE/CIN for about four times the speed (tolerance-level parity, MU level still exact;
+``'fast-relaxed'`` keeps the reference's iteration and is about 1.8x faster).
 """
 from functools import reduce
 
