@@ -125,6 +125,7 @@ class CapeWorkload:
         d = make_soundings(self.cfg, seed=CONFIGS[self.cfg]['seed'] + rank, cols=(0, cols) if cols else None,
                            winds=False, **kw)
         self.p1d = d['p'].ndim == 1
+        self.roofline_launches = 2 if self.p1d else 1     # pressure grids: + the 37-thread Exner-table kernel (~2 us)
         self.ncol, self.nlev = d['t'].shape
         if not self.p1d:
             self.fields3 = ('p', 't', 'td')

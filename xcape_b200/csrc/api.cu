@@ -146,6 +146,12 @@ int cape_device(const void* p, const void* t, const void* td, const void* ps, co
     if ((rc = launch_pres_lev_pos(p, ps, dtype, ncol, nlev, st, s))) return rc;   // in the inputs' own dtype
     a.start = st;
   }
+  if (p_is_1d) {          // Exner function of the shared pressure axis, once per call
+    float* pl;
+    XC_CUDA(sc.alloc(&pl, (size_t)nlev));
+    if ((rc = launch_exner_table(a.p, pl, nlev, s))) return rc;
+    a.pl_pi = pl;
+  }
   a.ncol = ncol; a.ld = ld; a.nlev = nlev; a.pinc = pinc; a.ml_depth = ml_depth;
   a.cape = cape; a.cin = cin; a.zout = zmulev; a.mulvl = mulev; a.status = status; a.n_iter = n_iter;
   if (precision == XCAPE_FAITHFUL) return launch_cape_faithful(a, source, adiabat, p_is_1d != 0, s);

@@ -55,6 +55,14 @@ static int launch_adiabat(const CapeArgs& a, int adiabat, cudaStream_t s) {
   return fail(XCAPE_ERR_ARG, "adiabat must be 1..4");
 }
 
+#if !defined(XC_FAST_TU) && !defined(XC_FAST_RELAXED_TU)
+int launch_exner_table(const float* p_hpa, float* pi, int nlev, cudaStream_t s) {
+  exner_table_kernel<MathSpec><<<(nlev + 127) / 128, 128, 0, s>>>(p_hpa, pi, nlev);
+  XC_LAUNCH_CHECK();
+  return XCAPE_OK;
+}
+#endif
+
 int XC_LAUNCH_NAME(const CapeArgs& a, int source, int adiabat, bool p1d, cudaStream_t s) {
   switch (source) {
     case 1: return p1d ? launch_adiabat<1, true>(a, adiabat, s) : launch_adiabat<1, false>(a, adiabat, s);
