@@ -219,6 +219,7 @@ class SrhWorkload:
     roofline_launches = 2        # streaming kernel + the (normally empty, ~3 us) EXACT work-list kernel
     KEYS3 = ('p', 't', 'td', 'u', 'v')
     KEYS1 = ('ps', 'ts', 'tds', 'us', 'vs')
+    precision = 'faithful'
 
     def __init__(self, cfg, metric, workload):
         self.cfg, self.metric, self.workload = cfg, metric, workload
@@ -232,6 +233,7 @@ class SrhWorkload:
 
     def _call(self, a, output=1, **kw):
         from xcape_b200.srh_cuda import srh_fused
+        kw.setdefault('precision', self.precision)
         return srh_fused(a['p'], a['t'], a['td'], a['u'], a['v'], a['ps'], a['ts'], a['tds'], a['us'], a['vs'],
                          0, None, 3000, 2., 1, output, **kw)
 
@@ -284,7 +286,7 @@ class SrhWorkload:
                 'traffic': ncu_traffic('srh_' + self.cfg, self.ncol),
                 'kernel': 'srh_kernel<float,false,false> (+ srh_exact_kernel on an empty work list)', 'kernel_ms': ms_kernel, 'bytes_per_column': self.bytes_per_col,
                 'peak_source': hbm_src, 'fp64_peak_tflops': fp64_peak,
-                'note': 'faithful mode evaluates the hypsometric exp/log chain in binary64 (reference arithmetic)'}
+                'note': 'faithful: hypsometric exp/log chain in binary64 (reference arithmetic); fast: binary32'}
 
 
 def ncu_traffic(key, ncol):

@@ -502,3 +502,21 @@ def test_fast_mode_on_edge_columns(core, oracle_mod, precision):
             gave_up = cnt['status'] == 2
             print(f'{source}: reference gives up on {gave_up.sum()} columns; secant solve converges on '
                   f'{(got[4][gave_up] == 0).sum()} of them')
+
+
+@pytest.mark.parametrize('cfg,vertical_lev', [('C3', 'sigma'), ('C2', 'pressure')])
+def test_srh_fast_precision(core, oracle_mod, cfg, vertical_lev):
+    """calc_srh(precision='fast'): binary32 height chain; inside max(1, 1e-4 rel) m2/s2 of the reference
+    chain by three orders of magnitude (SURVEY §8d probe: 1.2e-3), storm motion to 1e-3 m/s."""
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings(cfg, cols=(0, 50000))
+    args = tuple(d[k] for k in ('p', 't', 'td', 'u', 'v', 'ps', 'ts', 'tds', 'us', 'vs'))
+    got = core.calc_srh(*args, depth=3000, vertical_lev=vertical_lev, output_var='all', method='cuda', precision='fast')
+    ref = oracle_mod.calc_srh_ref(*args, depth=3000, vertical_lev=vertical_lev, output_var='all', nthreads=8)
+    dmax = max(np.abs(g - r).max() for g, r in zip(got[:2], ref[:2]))
+    print(f'{cfg}: fast SRH max|d| {dmax:.2e} m2/s2, storm motion max|d| {max(np.abs(g - r).max() for g, r in zip(got[2:], ref[2:])):.2e} m/s')
+    assert dmax < 2e-2
+    for g, r in zip(got[:2], ref[:2]):
+        assert tol_ok(g, r).all()
+    for g, r in zip(got[2:], ref[2:]):
+        assert np.abs(g - r).max() < 2e-3

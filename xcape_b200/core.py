@@ -247,7 +247,7 @@ def _calc_srh_gufunc(*args, **kwargs):
 
 
 def _calc_srh_numpy(*args, depth=3000, vertical_lev='sigma', output_var='srh', method='cuda',
-                    lev_axis=-1, device=0, devices=None, stream=None):
+                    lev_axis=-1, device=0, devices=None, stream=None, precision='faithful'):
     """Flatten, dispatch, unflatten (core.py:473-542).  ``aglh0 = 2.`` as in core.py:519."""
     p, t, td, u, v, ps, ts, tds, us, vs = (_as_array(a) for a in args)
     lev_axis = 0 if lev_axis == 0 else -1
@@ -270,7 +270,7 @@ def _calc_srh_numpy(*args, depth=3000, vertical_lev='sigma', output_var='srh', m
     if method == 'cuda':
         from .srh_cuda import srh_fused
         outs = srh_fused(p_2d, t_2d, td_2d, u_2d, v_2d, *surf, flag_1d, None, depth, 2., type_grid, output,
-                         device=device, devices=devices, stream=stream)
+                         device=device, devices=devices, stream=stream, precision=precision)
     elif method == 'fortran':
         _, srh_f, stdh_f = _reference_shims()
         host = [A.to_host_numpy(a) for a in (p_2d, t_2d, td_2d, u_2d, v_2d, *surf)]

@@ -178,9 +178,10 @@ template <class T>
 int srh_device_t(const void* p, const void* t, const void* td, const void* u, const void* v, const void* ps,
                  const void* ts, const void* tds, const void* us, const void* vs, int64_t ncol, int nlev, int p_is_1d,
                  int dtype, int layout, int64_t ld_in, double depth, double aglh0, const int32_t* start_3d,
-                 double* srh_rm, double* srh_lm, float* rm, float* lm, float* mean6, cudaStream_t s) {
+                 double* srh_rm, double* srh_lm, float* rm, float* lm, float* mean6, int precision, cudaStream_t s) {
   Scratch sc(s);
   SrhArgs<T> a{};
+  a.fast_heights = (precision == XCAPE_FAST);
   int rc;
   const void* q;
   int64_t ld = ncol, l2 = ncol;
@@ -582,7 +583,7 @@ int xcape_cuda_srh(const void* p, const void* t, const void* td, const void* u, 
                    int precision, int device, void* stream) {
   int rc = check_common(ncol, nlev, dtype, layout, mem);
   if (rc) return rc;
-  if (precision != XCAPE_FAITHFUL) return fail(XCAPE_ERR_ARG, "unknown precision mode");
+  if (precision != XCAPE_FAITHFUL && precision != XCAPE_FAST) return fail(XCAPE_ERR_ARG, "srh: precision must be XCAPE_FAITHFUL or XCAPE_FAST");
   if (ncol == 0) return XCAPE_OK;
   if (!p || !t || !td || !u || !v || !ps || !ts || !tds || !us || !vs || !srh_rm || !srh_lm) return fail(XCAPE_ERR_ARG, "null pointer");
   DeviceGuard dg(device);
@@ -592,9 +593,9 @@ int xcape_cuda_srh(const void* p, const void* t, const void* td, const void* u, 
                  const int32_t* st_, double* srm_, double* slm_, float* rm_, float* lm_, float* m6_, cudaStream_t s) {
     if (dtype == XCAPE_F64)
       return srh_device_t<double>(p_, t_, td_, u_, v_, ps_, ts_, tds_, us_, vs_, n, nlev, p_is_1d, dtype, layout, ld_in, depth,
-                                  aglh0, st_, srm_, slm_, rm_, lm_, m6_, s);
+                                  aglh0, st_, srm_, slm_, rm_, lm_, m6_, precision, s);
     return srh_device_t<float>(p_, t_, td_, u_, v_, ps_, ts_, tds_, us_, vs_, n, nlev, p_is_1d, dtype, layout, ld_in, depth,
-                               aglh0, st_, srm_, slm_, rm_, lm_, m6_, s);
+                               aglh0, st_, srm_, slm_, rm_, lm_, m6_, precision, s);
   };
   if (mem == XCAPE_MEM_DEVICE)
     return dev(p, t, td, u, v, ps, ts, tds, us, vs, ncol, ncol, start_3d, srh_rm, srh_lm, rm, lm, mean6, (cudaStream_t)stream);

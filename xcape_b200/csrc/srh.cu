@@ -15,14 +15,19 @@ int launch_srh_t(const SrhArgs<T>& a, bool p1d, cudaStream_t s) {
   const unsigned blocks = (unsigned)((a.ncol + 127) / 128);
   if (a.ncol >= (int64_t)1 << 31) return fail(XCAPE_ERR_ARG, "srh: more than 2^31-1 columns per call");
   XC_CUDA(cudaMemsetAsync(a.work_count, 0, sizeof(int), s));
-  if (a.aglh) srh_kernel<T, false, true><<<blocks, 128, 0, s>>>(a);
-  else if (p1d) srh_kernel<T, true, false><<<blocks, 128, 0, s>>>(a);
-  else srh_kernel<T, false, false><<<blocks, 128, 0, s>>>(a);
+  const bool fh = a.fast_heights != 0;
+  if (a.aglh) srh_kernel<T, false, true, false><<<blocks, 128, 0, s>>>(a);
+  else if (p1d && fh) srh_kernel<T, true, false, true><<<blocks, 128, 0, s>>>(a);
+  else if (p1d) srh_kernel<T, true, false, false><<<blocks, 128, 0, s>>>(a);
+  else if (fh) srh_kernel<T, false, false, true><<<blocks, 128, 0, s>>>(a);
+  else srh_kernel<T, false, false, false><<<blocks, 128, 0, s>>>(a);
   XC_LAUNCH_CHECK();
   const unsigned eb = (unsigned)std::min<int64_t>(blocks, 148 * 4);   // grid-stride over the (usually empty) work list
-  if (a.aglh) srh_exact_kernel<T, false, true><<<eb, 128, 0, s>>>(a);
-  else if (p1d) srh_exact_kernel<T, true, false><<<eb, 128, 0, s>>>(a);
-  else srh_exact_kernel<T, false, false><<<eb, 128, 0, s>>>(a);
+  if (a.aglh) srh_exact_kernel<T, false, true, false><<<eb, 128, 0, s>>>(a);
+  else if (p1d && fh) srh_exact_kernel<T, true, false, true><<<eb, 128, 0, s>>>(a);
+  else if (p1d) srh_exact_kernel<T, true, false, false><<<eb, 128, 0, s>>>(a);
+  else if (fh) srh_exact_kernel<T, false, false, true><<<eb, 128, 0, s>>>(a);
+  else srh_exact_kernel<T, false, false, false><<<eb, 128, 0, s>>>(a);
   XC_LAUNCH_CHECK();
   return XCAPE_OK;
 }

@@ -49,6 +49,7 @@ struct SrhArgs {
   float* __restrict__ rm;       // [2*ncol] or nullptr
   float* __restrict__ lm;
   float* __restrict__ mean6;
+  int fast_heights;                  // precision == XCAPE_FAST: binary32 height chain
   int32_t* __restrict__ work_list;   // [ncol] scratch: columns deferred to the EXACT kernel
   int* __restrict__ work_count;      // zeroed by the launcher
 };
@@ -82,6 +83,20 @@ __device__ __forceinline__ double tvirt(double T, double Td, double P) {
   const double x = hc::c2 - ddiv_fast(6808.0, Tdin) - hc::c3 * spec_log_d(Tdin);
   const double E = hc::c1 * spec_exp_d(x);
   return ddiv_fast(Tin * P, P - (1.0 - hc::eps) * E);
+}
+// precision = XCAPE_FAST: the same chain in binary32 on the FP32/XU pipes (MUFU.LG2/EX2/RCP).  The
+// SURVEY's probe (§8d) puts an all-binary32 height -> Bunkers -> SRH chain within 1.2e-3 m2/s2 of the
+// reference — three orders inside max(1, 1e-4 rel); heights are still accumulated in binary64.
+__device__ __forceinline__ float rcpf_(float b) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b)); return r; }
+__device__ __forceinline__ float tvirt_f(float T, float Td, float P) {
+  const float Tin = T + 273.15f, Tdin = Td + 273.15f;
+  const float x = 53.49f - 6808.0f * rcpf_(Tdin) - 5.09f * __logf(Tdin);
+  const float E = 6.112f * __expf(x);
+  return Tin * P * rcpf_(P - (1.0f - 0.6219800858985514f) * E);
+}
+__device__ __forceinline__ double hyps_step_f(double Hp, float Tv, float Tvp, float P, float Pp) {
+  const float dz = (287.04f * (0.5f * (Tv + Tvp)) * (1.0f / -9.80665f)) * __logf(P * rcpf_(Pp));
+  return Hp + (double)dz;
 }
 // one hypsometric step, f90:143,152:  H = Hp + (R (Tv+Tvp)/2 / g) ln(P/Pp), with ln(P/Pp) = ln P - ln Pp
 __device__ __forceinline__ double hyps_step(double Hp, double Tv, double Tvp, double lnP, double lnPp) {
@@ -120,7 +135,7 @@ __device__ __forceinline__ double ld_p(const SrhArgs<T>& a, int64_t c, int lev) 
 // being integrated from p, t, td — the reference's separate srh.srh call (srh.py:4).
 // The EXACT instantiation is kept out of line so that its 26 sample registers and second height
 // pass do not inflate the register count (and lower the occupancy) of the streaming path.
-template <class T, bool P1D, bool EXACT, bool HG>
+template <class T, bool P1D, bool EXACT, bool HG, bool FH = false>
 __device__ __forceinline__ bool srh_column(const SrhArgs<T>& a, int64_t c, int ks, SrhOut& o) {
   const int n3 = a.nlev - ks + 1;                 // 3-D levels used
   double Tvp = 0.0, Pp = 0.0, lnPp = 0.0, Hp;
@@ -128,8 +143,8 @@ __device__ __forceinline__ bool srh_column(const SrhArgs<T>& a, int64_t c, int k
     Hp = (double)a.aglhs[c];
   } else {
     const double Ps = (double)a.ps[c];
-    Tvp = tvirt((double)a.ts[c], (double)a.tds[c], Ps);
-    Hp = a.aglh0; Pp = Ps; lnPp = spec_log_d(Ps);
+    Tvp = FH ? (double)tvirt_f((float)a.ts[c], (float)a.tds[c], (float)Ps) : tvirt((double)a.ts[c], (double)a.tds[c], Ps);
+    Hp = a.aglh0; Pp = Ps; lnPp = FH ? 0.0 : spec_log_d(Ps);
   }
   const double Hs = Hp;
   double up = (double)a.us[c], vp = (double)a.vs[c];
@@ -148,7 +163,7 @@ __device__ __forceinline__ bool srh_column(const SrhArgs<T>& a, int64_t c, int k
   bool descending = false;
   if (EXACT) {
     // DINTERP2DZ orientation test Z(1) > Z(NZ) needs the top height first (f90:211-216)
-    double H = Hp, Tv0 = Tvp, lnP0 = lnPp;
+    double H = Hp, Tv0 = Tvp, lnP0 = FH ? Pp : lnPp;
     if (HG) {
       H = (double)a.aglh[(int64_t)(ks - 1 + n3 - 1) * a.ld + c];
     } else {
@@ -156,10 +171,16 @@ __device__ __forceinline__ bool srh_column(const SrhArgs<T>& a, int64_t c, int k
         const int lev = ks - 1 + i;
         const int64_t off = (int64_t)lev * a.ld + c;
         const double P = ld_p<T, P1D>(a, c, lev);
-        const double Tv = tvirt((double)a.t[off], (double)a.td[off], P);
-        const double lnP = spec_log_d(P);
-        H = hyps_step(H, Tv, Tv0, lnP, lnP0);
-        Tv0 = Tv; lnP0 = lnP;
+        if (FH) {
+          const float Tvf = tvirt_f((float)a.t[off], (float)a.td[off], (float)P);
+          H = hyps_step_f(H, Tvf, (float)Tv0, (float)P, (float)lnP0);      // lnP0 carries the previous P here
+          Tv0 = Tvf; lnP0 = P;
+        } else {
+          const double Tv = tvirt((double)a.t[off], (double)a.td[off], P);
+          const double lnP = spec_log_d(P);
+          H = hyps_step(H, Tv, Tv0, lnP, lnP0);
+          Tv0 = Tv; lnP0 = lnP;
+        }
       }
     }
     descending = ((float)Hs > (float)H);
@@ -180,9 +201,14 @@ __device__ __forceinline__ bool srh_column(const SrhArgs<T>& a, int64_t c, int k
     } else {
       P = ld_p<T, P1D>(a, c, lev);
       if (!(P < Pp)) mono = false;
-      Tv = tvirt((double)a.t[off], (double)a.td[off], P);
-      lnP = spec_log_d(P);
-      H = hyps_step(Hp, Tv, Tvp, lnP, lnPp);                    // stdheight_2D_model_lev.f90:143,152
+      if (FH) {
+        Tv = (double)tvirt_f((float)a.t[off], (float)a.td[off], (float)P);
+        H = hyps_step_f(Hp, (float)Tv, (float)Tvp, (float)P, (float)Pp);
+      } else {
+        Tv = tvirt((double)a.t[off], (double)a.td[off], P);
+        lnP = spec_log_d(P);
+        H = hyps_step(Hp, Tv, Tvp, lnP, lnPp);                  // stdheight_2D_model_lev.f90:143,152
+      }
     }
     const double uk = (double)uin, vk = (double)vin;
     const float ukf = (float)uin, vkf = (float)vin, zkf = (float)H;
@@ -281,18 +307,18 @@ __device__ __forceinline__ void srh_store(const SrhArgs<T>& a, int64_t c, const 
 // Streaming pass.  Columns that need the literal DINTERP2DZ search (non-monotone pressure /
 // heights) are appended to a work list and left to srh_exact_kernel, so that the EXACT code's
 // registers (13 + 13 samples, second height pass) never limit this kernel's occupancy.
-template <class T, bool P1D, bool HG>
+template <class T, bool P1D, bool HG, bool FH>
 __global__ void __launch_bounds__(128) srh_kernel(const SrhArgs<T> a) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.ncol) return;
   int ks = a.start ? a.start[c] : 1;
   ks = ks < 1 ? 1 : (ks > a.nlev ? a.nlev : ks);
   SrhOut o;
-  if (srh_column<T, P1D, false, HG>(a, c, ks, o)) srh_store(a, c, o);
+  if (srh_column<T, P1D, false, HG, FH>(a, c, ks, o)) srh_store(a, c, o);
   else a.work_list[atomicAdd(a.work_count, 1)] = (int32_t)c;
 }
 
-template <class T, bool P1D, bool HG>
+template <class T, bool P1D, bool HG, bool FH>
 __global__ void __launch_bounds__(128) srh_exact_kernel(const SrhArgs<T> a) {
   const int n = *a.work_count;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -300,7 +326,7 @@ __global__ void __launch_bounds__(128) srh_exact_kernel(const SrhArgs<T> a) {
     int ks = a.start ? a.start[c] : 1;
     ks = ks < 1 ? 1 : (ks > a.nlev ? a.nlev : ks);
     SrhOut o;
-    srh_column<T, P1D, true, HG>(a, c, ks, o);
+    srh_column<T, P1D, true, HG, FH>(a, c, ks, o);
     srh_store(a, c, o);
   }
 }

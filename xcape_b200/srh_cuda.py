@@ -17,16 +17,20 @@ from .sharding import column_blocks, run_on_devices
 
 
 def srh_fused(p_2d, t_2d, td_2d, u_2d, v_2d, p_s, t_s, td_s, u_s, v_s, flag_1d, pres_lev_pos, depth,
-              aglh0, type_grid, output, *, device=0, devices=None, stream=None):
+              aglh0, type_grid, output, *, device=0, devices=None, stream=None, precision='faithful'):
     """
     Arguments are the union of ``stdheight.stdheight`` (stdheight.py:5) and ``srh.srh``
     (srh.py:4): ``*_2d`` are ``(nlev, ngrid)``, ``*_s`` are ``(ngrid,)``; ``pres_lev_pos`` may be
     ``None`` (computed on the device for pressure grids); ``aglh0`` is the scalar height of the
     surface level (core.py:519 passes 2.0); ``output`` 1 -> ``(srh_rm, srh_lm)``, otherwise
     ``(srh_rm, srh_lm, rm(2, ngrid), lm(2, ngrid), mean_6km(2, ngrid))`` like srh.py:63-66.
-    srh_* are float64, the storm-motion arrays float32.
+    srh_* are float64, the storm-motion arrays float32.  ``precision='fast'``
+    evaluates the hypsometric height chain in binary32 (within ~1e-3 m2/s2 of the reference).
     """
     L = _lib.lib()
+    if precision not in ('faithful', 'fast'):
+        raise ValueError("precision must be 'faithful' or 'fast'")
+    prec = _lib.PRECISION[precision]
     nlev, ngrid = t_2d.shape
     if type_grid == 1:
         p_is_1d = 0
@@ -87,7 +91,7 @@ def srh_fused(p_2d, t_2d, td_2d, u_2d, v_2d, p_s, t_s, td_s, u_s, v_s, flag_1d, 
             off1(ps_, es), off1(ts_, es), off1(tds_, es), off1(us_, es), off1(vs_, es),
             C.c_int64(n), nlev, p_is_1d, dt, layout, mem, C.c_double(float(depth)), C.c_double(float(aglh0)),
             off1(start, 4), off1(srm, 8), off1(slm, 8), off1(rm, 8), off1(lm, 8), off1(m6, 8),
-            _lib.FAITHFUL, dev, A.stream_of(ref, stream))
+            prec, dev, A.stream_of(ref, stream))
         _lib.check(rc)
 
     if mem == _lib.MEM_HOST and devices is not None and len(devices) > 1:
