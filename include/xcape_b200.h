@@ -57,7 +57,10 @@ enum { XCAPE_FAITHFUL = 0,
        XCAPE_FAST_RELAXED = 2 };
 /* per-column status word (optional output) */
 enum { XCAPE_ST_OK = 0, XCAPE_ST_SKIPPED = 1 /* ts <= 0 degC gate, f90:77 */,
-       XCAPE_ST_NONCONVERGED = 2 /* > 100 moist iterations, f90:464-474: cape = cin = 0 */ };
+       XCAPE_ST_NONCONVERGED = 2 /* > 100 moist iterations, f90:464-474: cape = cin = 0 */,
+       XCAPE_ST_INVALID = 3 /* non-finite / absurd pressure step (fill values, NaN) or > 2^22 moist passes:
+                               cape = cin = 0; the reference has undefined behaviour here (int overflow).
+                               Guarantees that no input can make a thread spin. */ };
 
 /* ---------------------------------------------------------------------------------------
  * CAPE / CIN.  Replaces loopcape_ml (CAPE_CODE_model_lev.pyf:6-24, f90:4-91) when

@@ -184,7 +184,9 @@ template <int TM> inline float getthe(float p, float t, float td, float q) {   /
 
 struct ColOut { float cape, cin, zout; int32_t mulvl; int32_t n_iter, n_sub, status; };
 enum { ST_OK = 0, ST_SKIPPED = 1, ST_NONCONV = 2 };
-constexpr int NLOOP_CAP = 1 << 20;   // guard for garbage dp/pinc (documented; unreachable on valid data)
+constexpr int NLOOP_CAP = 1 << 16;     // sub-steps per layer beyond this, or a NaN step => status 3 (invalid sounding)
+constexpr int ITER_BUDGET = 1 << 22;   // moist passes per column beyond this => status 3
+enum { ST_INVALID = 3 };
 
 // One column.  pA/tA/tdA hold nk_in levels with stride `ls` (elements).
 template <int TM>
@@ -299,7 +301,9 @@ void getcape(const float* pA, const float* tA, const float* tdA, int64_t ls_p, i
       nloop = 1;
     } else {
       float r = dp / pinc;
-      nloop = (r < (float)NLOOP_CAP) ? 1 + (int)r : NLOOP_CAP;
+      // the reference overflows int(dp/pinc) here (undefined behaviour); documented deviation shared with the kernel
+      if (!(r < (float)NLOOP_CAP)) { o.cape = 0.0f; o.cin = 0.0f; o.status = ST_INVALID; return; }
+      nloop = 1 + (int)r;
       dp = dp / (float)nloop;
     }
     for (int n = 1; n <= nloop; ++n) {
@@ -339,6 +343,7 @@ void getcape(const float* pA, const float* tA, const float* tdA, int64_t ls_p, i
         if (std::fabs(th2 - thlast) > c_converge) thlast = thlast + 0.3f * (th2 - thlast);
         else not_converged = false;
       }
+      if (o.n_iter > ITER_BUDGET) { o.cape = 0.0f; o.cin = 0.0f; o.status = ST_INVALID; return; }
       if (pseudo) { qt = qv2; ql2 = 0.0f; qi2 = 0.0f; }          // f90:487-491
     }
     thv2 = th2 * (1.0f + c_reps * qv2) / (1.0f + qv2 + ql2 + qi2);   // f90:501-503

@@ -520,3 +520,49 @@ def test_srh_fast_precision(core, oracle_mod, cfg, vertical_lev):
         assert tol_ok(g, r).all()
     for g, r in zip(got[2:], ref[2:]):
         assert np.abs(g - r).max() < 2e-3
+
+
+# ------------------------------------------------------------------ garbage in: never hang, never crash
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize('vertical_lev', ['sigma', 'pressure'])
+def test_garbage_inputs_terminate_and_match_oracle(core, oracle_mod, vertical_lev):
+    """Fill values, NaN, inf, zero / negative / unordered pressures: every call returns promptly
+    (no thread may spin: status 3 guards), never raises, and — because oracle and kernel share the
+    arithmetic contract down to NaN propagation — still agrees with the oracle bit for bit."""
+    from xcape_b200.cape_cuda import cape as cape_cuda
+    from xcape_b200.synthetic import make_soundings
+    cfg = 'C3' if vertical_lev == 'sigma' else 'C2'
+    d = make_soundings(cfg, cols=(0, 4096))
+    rng = np.random.default_rng(5)
+    p, t, td, ps, ts, tds = (d[k].copy() for k in ('p', 't', 'td', 'ps', 'ts', 'tds'))
+    bad = [np.nan, np.inf, -np.inf, 9.96921e36, -9999.0, 0.0, -1.0, 1e-30]
+    for arr in (t, td) + ((p,) if vertical_lev == 'sigma' else ()):
+        idx = rng.integers(0, arr.size, 600)
+        arr.reshape(-1)[idx] = rng.choice(bad, idx.size).astype(np.float32)
+    for arr in (ps, ts, tds):
+        idx = rng.integers(0, arr.size, 200)
+        arr[idx] = rng.choice(bad, idx.size).astype(np.float32)
+    if vertical_lev == 'sigma':
+        p[7::50] = p[7::50][:, ::-1]                      # columns given top-down
+        p[11::64, 5:9] = 1e20                             # absurd pressure steps -> status 3
+    n_bad_status = 0
+    for source, src in (('surface', 1), ('most-unstable', 2), ('mixed-layer', 3)):
+        for precision in ('faithful', 'fast', 'fast-relaxed'):
+            p2 = p.T if vertical_lev == 'sigma' else p
+            got = cape_cuda(p2, t.T, td.T, ps, ts, tds, 1 if vertical_lev == 'pressure' else 0, None, src, 500., 1, 500.,
+                            1 if vertical_lev == 'sigma' else 2, precision=precision, return_counters=True)
+            assert set(np.unique(got[4])) <= {0, 1, 2, 3}
+            if precision != 'faithful':
+                continue
+            with np.errstate(all='ignore'):
+                ref, cnt = oracle_mod.calc_cape_ref(p, t, td, ps, ts, tds, source=source, pinc=500., vertical_lev=vertical_lev,
+                                                    tmode=oracle_mod.SPEC, counters=True, nthreads=8)
+            assert np.array_equal(got[4], cnt['status'])
+            n_bad_status += int((cnt['status'] == 3).sum())
+            for g, r, name in zip(got[:4], ref, ('cape', 'cin', 'mulev', 'zmulev')):
+                assert np.array_equal(g, r, equal_nan=(name != 'mulev')), f'{vertical_lev} {source}: {name}'
+    if vertical_lev == 'sigma':
+        assert n_bad_status > 0
+    # SRH on the same garbage: must return
+    u = d['u'].copy(); v = d['v'].copy()
+    core.calc_srh(p, t, td, u, v, ps, ts, tds, d['us'], d['vs'], vertical_lev=vertical_lev, output_var='all', method='cuda')
