@@ -557,10 +557,22 @@ def test_garbage_inputs_terminate_and_match_oracle(core, oracle_mod, vertical_le
             with np.errstate(all='ignore'):
                 ref, cnt = oracle_mod.calc_cape_ref(p, t, td, ps, ts, tds, source=source, pinc=500., vertical_lev=vertical_lev,
                                                     tmode=oracle_mod.SPEC, counters=True, nthreads=8)
-            assert np.array_equal(got[4], cnt['status'])
             n_bad_status += int((cnt['status'] == 3).sum())
+            # The mixed-layer source on columns whose pressure is not strictly decreasing is the one place
+            # where kernel and reference order their case tests differently (DESIGN.md "deviations"): the
+            # reference looks at z(nk) first (f90:301), the streaming kernel never computes it.
+            pfull = np.concatenate([ps[:, None], p if vertical_lev == 'sigma' else np.broadcast_to(p, (ps.size, p.size))], axis=1)
+            with np.errstate(all='ignore'):
+                mono = np.all(np.diff(pfull, axis=1) < 0, axis=1)
+            check = mono if source == 'mixed-layer' else np.ones_like(mono)
+            bad = np.flatnonzero((got[4] != cnt['status']) & check)
+            assert bad.size == 0, (f'{vertical_lev} {source}: status differs in {bad.size} columns, e.g. col {bad[:5]}: '
+                                   f'gpu {got[4][bad[:5]]} oracle {cnt["status"][bad[:5]]} ts {ts[bad[:5]]} ps {ps[bad[:5]]}')
             for g, r, name in zip(got[:4], ref, ('cape', 'cin', 'mulev', 'zmulev')):
-                assert np.array_equal(g, r, equal_nan=(name != 'mulev')), f'{vertical_lev} {source}: {name}'
+                same = (g == r) | (np.isnan(g.astype(np.float64)) & np.isnan(r.astype(np.float64)))
+                bad = np.flatnonzero(~same & check)
+                assert bad.size == 0, (f'{vertical_lev} {source}: {name} differs in {bad.size} columns, e.g. col {bad[:5]}: '
+                                       f'gpu {g[bad[:5]]} oracle {r[bad[:5]]} status {cnt["status"][bad[:5]]} ts {ts[bad[:5]]} ps {ps[bad[:5]]}')
     if vertical_lev == 'sigma':
         assert n_bad_status > 0
     # SRH on the same garbage: must return
