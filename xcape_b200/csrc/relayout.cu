@@ -14,6 +14,9 @@ namespace xc {
 // (37, 50, 137 ...); the run is parked in shared memory with an odd row stride (no bank
 // conflicts on the transposed read) and written out as nlev rows of TC consecutive columns.
 constexpr int kTC = 64;
+
+template <class T> struct Vec4 { T x, y, z, w; };
+
 template <class T, class TO>
 __global__ void __launch_bounds__(256) transpose_cast_kernel(const T* __restrict__ in, TO* __restrict__ out,
                                                              int64_t ncol, int nlev, int64_t ld) {
@@ -24,15 +27,43 @@ __global__ void __launch_bounds__(256) transpose_cast_kernel(const T* __restrict
   const int nc = (int)min((int64_t)kTC, ncol - c0);
   const int nelem = nc * nlev;
   const T* src = in + c0 * nlev;
-  for (int i = threadIdx.x; i < nelem; i += blockDim.x) {
-    const int c = i / nlev, l = i - c * nlev;
-    tile[c * S + l] = (TO)src[i];
+  // ---- read: the block's columns are one contiguous run; 4 elements per load when the run is
+  // 4-element aligned (always for full blocks: kTC*nlev is a multiple of 4 and cudaMalloc'ed
+  // bases are 256-byte aligned), one index division per 4 elements.
+  const bool vec_in = ((reinterpret_cast<uintptr_t>(src) & (4 * sizeof(T) - 1)) == 0) && ((nelem & 3) == 0);
+  if (vec_in) {
+    const Vec4<T>* src4 = reinterpret_cast<const Vec4<T>*>(src);
+    for (int q = threadIdx.x; q < (nelem >> 2); q += blockDim.x) {
+      const Vec4<T> v = src4[q];
+      const int i = q << 2;
+      int c = i / nlev, l = i - c * nlev;
+      tile[c * S + l] = (TO)v.x; if (++l == nlev) { l = 0; ++c; }
+      tile[c * S + l] = (TO)v.y; if (++l == nlev) { l = 0; ++c; }
+      tile[c * S + l] = (TO)v.z; if (++l == nlev) { l = 0; ++c; }
+      tile[c * S + l] = (TO)v.w;
+    }
+  } else {
+    for (int i = threadIdx.x; i < nelem; i += blockDim.x) {
+      const int c = i / nlev, l = i - c * nlev;
+      tile[c * S + l] = (TO)src[i];
+    }
   }
   __syncthreads();
-  // write: consecutive threads -> consecutive columns of one level row
-  for (int i = threadIdx.x; i < nlev * kTC; i += blockDim.x) {
-    const int l = i / kTC, c = i - l * kTC;
-    if (c < nc) out[(int64_t)l * ld + c0 + c] = tile[c * S + l];
+  // ---- write: one warp stores one level row of the block (kTC = 64 consecutive columns) per
+  // instruction, two columns per lane, when the row start is 2-element aligned.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const bool vec_out = (nc == kTC) && ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & (2 * sizeof(TO) - 1)) == 0);
+  if (vec_out) {
+    struct alignas(2 * sizeof(TO)) Pair { TO a, b; };
+    for (int l = warp; l < nlev; l += nwarp) {
+      Pair pr;
+      pr.a = tile[(2 * lane) * S + l];
+      pr.b = tile[(2 * lane + 1) * S + l];
+      *reinterpret_cast<Pair*>(out + (int64_t)l * ld + c0 + 2 * lane) = pr;
+    }
+  } else {
+    for (int l = warp; l < nlev; l += nwarp)
+      for (int c = lane; c < nc; c += 32) out[(int64_t)l * ld + c0 + c] = tile[c * S + l];
   }
 }
 
