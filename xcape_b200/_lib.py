@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libxcape_b200.so')
+LIB_PATH = os.environ.get('XCAPE_B200_LIB') or os.path.join(_HERE, 'libxcape_b200.so')   # env override: A/B experiments
 
 # enums of include/xcape_b200.h
 F32, F64 = 0, 1
