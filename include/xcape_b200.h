@@ -26,6 +26,12 @@
 
 #include <stdint.h>
 
+#if defined(__GNUC__)
+#define XCAPE_API __attribute__((visibility("default")))
+#else
+#define XCAPE_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -82,7 +88,7 @@ enum { XCAPE_ST_OK = 0, XCAPE_ST_SKIPPED = 1 /* ts <= 0 degC gate, f90:77 */,
  *            the call stages column blocks through pinned buffers, overlaps copies with
  *            compute, and returns when the outputs are complete (`stream` is ignored).
  * ------------------------------------------------------------------------------------- */
-int xcape_cuda_cape(const void* p, const void* t, const void* td,
+XCAPE_API int xcape_cuda_cape(const void* p, const void* t, const void* td,
                     const void* ps, const void* ts, const void* tds,
                     int64_t ncol, int nlev, int p_is_1d, int dtype, int layout, int mem,
                     int source, int adiabat, float ml_depth, float pinc,
@@ -102,7 +108,7 @@ int xcape_cuda_cape(const void* p, const void* t, const void* td,
  *                   column i at [2*i + c]) or NULL (output_var == 'srh')
  *   aglh0           height of the surface level (core.py passes 2.0)
  * ------------------------------------------------------------------------------------- */
-int xcape_cuda_srh(const void* p, const void* t, const void* td, const void* u, const void* v,
+XCAPE_API int xcape_cuda_srh(const void* p, const void* t, const void* td, const void* u, const void* v,
                    const void* ps, const void* ts, const void* tds, const void* us, const void* vs,
                    int64_t ncol, int nlev, int p_is_1d, int dtype, int layout, int mem,
                    double depth, double aglh0, const int32_t* start_3d,
@@ -114,7 +120,7 @@ int xcape_cuda_srh(const void* p, const void* t, const void* td, const void* u, 
  * srh.srh chains them (srh.py:41-61): u, v, aglh 3-D fields, us, vs, aglhs [ncol]; levels below
  * start_3d (NULL = 1) are ignored.  Heights are used as binary64 by the helicity sum and
  * down-cast to binary32 by the Bunkers part, like the f2py casts do. */
-int xcape_cuda_srh_from_heights(const void* u, const void* v, const void* aglh,
+XCAPE_API int xcape_cuda_srh_from_heights(const void* u, const void* v, const void* aglh,
                                 const void* us, const void* vs, const void* aglhs,
                                 int64_t ncol, int nlev, int dtype, int layout, int mem,
                                 double depth, const int32_t* start_3d,
@@ -124,7 +130,7 @@ int xcape_cuda_srh_from_heights(const void* u, const void* v, const void* aglh,
 /* Heights only (loop_stdheight_ml / loop_stdheight_pl1d).  h is float64, same layout as the
  * inputs' `layout`; levels below start_3d are -999999 (stdheight_2D_pressure_lev.f90:85-87);
  * hs [ncol] = aglh0. */
-int xcape_cuda_stdheight(const void* p, const void* t, const void* td,
+XCAPE_API int xcape_cuda_stdheight(const void* p, const void* t, const void* td,
                          const void* ps, const void* ts, const void* tds,
                          int64_t ncol, int nlev, int p_is_1d, int dtype, int layout, int mem,
                          double aglh0, const int32_t* start_3d,
@@ -132,17 +138,17 @@ int xcape_cuda_stdheight(const void* p, const void* t, const void* td,
 
 /* core.py:286-289 on the device: start[i] = 1 + argmin_k { ps[i] - p[k] : ps[i] - p[k] >= 0 }
  * (first minimum; 1 when every level is masked), evaluated in the inputs' own dtype. */
-int xcape_cuda_pres_lev_pos(const void* p, const void* ps, int64_t ncol, int nlev, int dtype,
+XCAPE_API int xcape_cuda_pres_lev_pos(const void* p, const void* ps, int64_t ncol, int nlev, int dtype,
                             int mem, int32_t* start_3d, int device, void* stream);
 
 /* Diagnostics. */
-const char* xcape_cuda_last_error(void);      /* thread-local message of the last failure */
-int xcape_cuda_device_count(void);            /* < 0 on error */
-const char* xcape_cuda_version(void);         /* "xcape_b200 <semver> sm_100a" */
-int64_t xcape_cuda_kernel_launches(void);     /* kernels launched by this library so far (process-wide) */
+XCAPE_API const char* xcape_cuda_last_error(void);      /* thread-local message of the last failure */
+XCAPE_API int xcape_cuda_device_count(void);            /* < 0 on error */
+XCAPE_API const char* xcape_cuda_version(void);         /* "xcape_b200 <semver> sm_100a" */
+XCAPE_API int64_t xcape_cuda_kernel_launches(void);     /* kernels launched by this library so far (process-wide) */
 /* Measured arithmetic peaks of `device` (roofline denominators the driver's MEASURED_PEAKS.json
  * lacks): dependent-chain-free FFMA / DFMA loops, 2 flop per FMA, best of `reps` launches. */
-int xcape_cuda_measure_peaks(int device, int reps, double* fp32_tflops, double* fp64_tflops);
+XCAPE_API int xcape_cuda_measure_peaks(int device, int reps, double* fp32_tflops, double* fp64_tflops);
 
 #ifdef __cplusplus
 }

@@ -580,3 +580,40 @@ def test_garbage_inputs_terminate_and_match_oracle(core, oracle_mod, vertical_le
     # SRH on the same garbage: must return
     u = d['u'].copy(); v = d['v'].copy()
     core.calc_srh(p, t, td, u, v, ps, ts, tds, d['us'], d['vs'], vertical_lev=vertical_lev, output_var='all', method='cuda')
+
+
+# ------------------------------------------------------------------ thread safety (dask's threaded scheduler)
+def test_concurrent_calls_from_python_threads(core):
+    """The reference's f2py routines are `threadsafe` (GIL released) and dask's threaded scheduler calls
+    them concurrently, one block per thread.  Same here: 6 threads issue host-pointer CAPE and SRH calls
+    at once (ctypes drops the GIL); every result equals the serial one."""
+    import threading
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C3', cols=(0, 240_000))
+    kw = dict(source='mixed-layer', pinc=500., vertical_lev='sigma', method='cuda')
+    keys = ('p', 't', 'td', 'ps', 'ts', 'tds')
+    skeys = ('p', 't', 'td', 'u', 'v', 'ps', 'ts', 'tds', 'us', 'vs')
+    serial = core.calc_cape(*(d[k] for k in keys), **kw)
+    serial_srh = core.calc_srh(*(d[k] for k in skeys), vertical_lev='sigma', method='cuda')
+    blocks = [(i * 40_000, (i + 1) * 40_000) for i in range(6)]
+    out, errs = {}, []
+
+    def work(i, a, b):
+        try:
+            for rep in range(3):
+                out[i] = (core.calc_cape(*(d[k][a:b] for k in keys), **kw),
+                          core.calc_srh(*(d[k][a:b] for k in skeys), vertical_lev='sigma', method='cuda'))
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+
+    ths = [threading.Thread(target=work, args=(i, a, b)) for i, (a, b) in enumerate(blocks)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    for i, (a, b) in enumerate(blocks):
+        for g, r in zip(out[i][0], serial):
+            assert np.array_equal(g, r[a:b])
+        for g, r in zip(out[i][1], serial_srh):
+            assert np.array_equal(g, r[a:b])

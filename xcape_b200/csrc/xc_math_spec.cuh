@@ -16,11 +16,6 @@
 
 namespace xc {
 
-#define XC_SP_L2E    0x1.71547652b82fep+0   /* log2(e)            */
-#define XC_SP_LN2_HI 0x1.62e42fee00000p-1   /* fdlibm split, ln 2 */
-#define XC_SP_LN2_LO 0x1.a39ef35793c76p-33
-#define XC_SP_MAGIC  6755399441055744.0     /* 1.5 * 2^52         */
-
 // Polynomial / reduction constants live in constant memory: DFMA takes a c[bank][offset]
 // operand directly, whereas an immediate binary64 costs two UMOV issue slots per use
 // (ncu r1a: 40 of the 195 instructions of the moist-iteration body were such UMOVs).
