@@ -617,3 +617,40 @@ def test_concurrent_calls_from_python_threads(core):
             assert np.array_equal(g, r[a:b])
         for g, r in zip(out[i][1], serial_srh):
             assert np.array_equal(g, r[a:b])
+
+
+# ------------------------------------------------------------------ full-size properties of the other configs
+@pytest.mark.parametrize('cfg', ['C3', 'C4', 'C5'])
+def test_full_size_configs_properties(core, cfg):
+    """BASELINE configs 3-5 at full per-GPU size — C3: mixed-layer CAPE on HRRR 1059x1799x50; C4: SRH on the
+    same grid; C5: most-unstable CAPE on one 721x1440x137 time step of the stack (the stack is sharded by
+    time step).  Size-independent properties: finiteness, gate semantics, permutation equivariance (a
+    column's result depends on nothing but the column), and split invariance across the host path's
+    block boundaries."""
+    from xcape_b200.synthetic import make_soundings
+    kw = dict(grid=(721, 1440)) if cfg == 'C5' else {}
+    d = make_soundings(cfg, active=False, winds=(cfg == 'C4'), **kw)
+    ncol = d['t'].shape[0]
+    assert ncol == (721 * 1440 if cfg == 'C5' else 1059 * 1799)
+    rng = np.random.default_rng(3)
+    idx = rng.choice(ncol, 40_000, replace=False)
+    if cfg == 'C4':
+        keys = ('p', 't', 'td', 'u', 'v', 'ps', 'ts', 'tds', 'us', 'vs')
+        f = lambda a: core.calc_srh(*a, depth=3000, vertical_lev='sigma', output_var='all', method='cuda')   # noqa: E731
+    else:
+        keys = ('p', 't', 'td', 'ps', 'ts', 'tds')
+        src = 'mixed-layer' if cfg == 'C3' else 'most-unstable'
+        f = lambda a: core.calc_cape(*a, source=src, ml_depth=500., pinc=500., vertical_lev='sigma', method='cuda')   # noqa: E731
+    full = f([d[k] for k in keys])
+    assert all(np.isfinite(np.asarray(x, dtype=np.float64)).all() for x in full)
+    if cfg != 'C4':
+        gated = ~(d['ts'] > 0)
+        assert gated.any() and (full[0][gated] == 0).all() and (full[1][gated] == 0).all()
+        assert (full[0] >= 0).all() and (full[1] >= 0).all()
+    sub = f([d[k][idx] for k in keys])
+    for a, b in zip(sub, full):
+        assert np.array_equal(a, b[idx])
+    h = 262144 + 32768 + 77                      # not aligned with any block of the host ring
+    lo, hi = f([d[k][:h] for k in keys]), f([d[k][h:] for k in keys])
+    for a, b, c in zip(lo, hi, full):
+        assert np.array_equal(np.concatenate([a, b]), c)
