@@ -185,12 +185,19 @@ int srh_device_t(const void* p, const void* t, const void* td, const void* u, co
   int rc;
   const void* q;
   int64_t ld = ncol, l2 = ncol;
-  if ((rc = canon3d_same(t, dtype, layout, ncol, nlev, ld_in, sc, &q, &ld, s))) return rc; a.t = (const T*)q;
-  if ((rc = canon3d_same(td, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.td = (const T*)q;
-  if ((rc = canon3d_same(u, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.u = (const T*)q;
-  if ((rc = canon3d_same(v, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.v = (const T*)q;
-  if (p_is_1d) a.p = (const T*)p;
-  else { if ((rc = canon3d_same(p, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.p = (const T*)q; }
+  if (layout == XCAPE_LEVEL_LAST) {
+    // reference layout: no relayout pass — srh_tiled_kernel reads it through shared-memory tiles
+    a.t = (const T*)t; a.td = (const T*)td; a.u = (const T*)u; a.v = (const T*)v; a.p = (const T*)p;
+    a.lev_stride = 1; a.col_stride = nlev;
+  } else {
+    if ((rc = canon3d_same(t, dtype, layout, ncol, nlev, ld_in, sc, &q, &ld, s))) return rc; a.t = (const T*)q;
+    if ((rc = canon3d_same(td, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.td = (const T*)q;
+    if ((rc = canon3d_same(u, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.u = (const T*)q;
+    if ((rc = canon3d_same(v, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.v = (const T*)q;
+    if (p_is_1d) a.p = (const T*)p;
+    else { if ((rc = canon3d_same(p, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.p = (const T*)q; }
+    a.lev_stride = ld; a.col_stride = 1;
+  }
   a.ps = (const T*)ps; a.ts = (const T*)ts; a.tds = (const T*)tds; a.us = (const T*)us; a.vs = (const T*)vs;
   a.start = start_3d;
   if (p_is_1d && !start_3d) {
@@ -220,6 +227,7 @@ int srh_heights_device_t(const void* u, const void* v, const void* aglh, const v
   if ((rc = canon3d_same(aglh, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.aglh = (const T*)q;
   a.us = (const T*)us; a.vs = (const T*)vs; a.aglhs = (const T*)aglhs;
   a.start = start_3d;
+  a.lev_stride = ld; a.col_stride = 1;
   a.ncol = ncol; a.ld = ld; a.nlev = nlev; a.depth = depth; a.aglh0 = 0.0;
   a.srh_rm = srh_rm; a.srh_lm = srh_lm; a.rm = rm; a.lm = lm; a.mean6 = mean6;
   { int32_t* wl; int* wc; XC_CUDA(sc.alloc(&wl, (size_t)ncol)); XC_CUDA(sc.alloc(&wc, (size_t)1)); a.work_list = wl; a.work_count = wc; }

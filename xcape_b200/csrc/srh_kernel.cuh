@@ -42,6 +42,7 @@ struct SrhArgs {
   const T* __restrict__ aglhs;  // [ncol] height of the surface level when aglh is given
   const int32_t* __restrict__ start;   // 1-based or nullptr
   int64_t ncol, ld;
+  int64_t lev_stride, col_stride;      // element (lev, c) of a 3-D field at lev*lev_stride + c*col_stride
   int nlev;
   double depth, aglh0;
   double* __restrict__ srh_rm;
@@ -125,106 +126,94 @@ __device__ __forceinline__ void bunkers_finish(float mu, float mv, float s1u, fl
   o.m6u = mu; o.m6v = mv;
 }
 
+// Element (level lev, column c) of a 3-D field: level-major (lev_stride = ld, col_stride = 1) or the
+// reference's level-last layout (lev_stride = 1, col_stride = nlev; used by the EXACT kernel only —
+// the streaming path reads that layout through shared-memory tiles, see srh_tiled_kernel).
+template <class T>
+__device__ __forceinline__ int64_t off3(const SrhArgs<T>& a, int64_t c, int lev) {
+  return (int64_t)lev * a.lev_stride + c * a.col_stride;
+}
 template <class T, bool P1D>
 __device__ __forceinline__ double ld_p(const SrhArgs<T>& a, int64_t c, int lev) {
-  return (double)(P1D ? __ldg(a.p + lev) : a.p[(int64_t)lev * a.ld + c]);
+  return (double)(P1D ? __ldg(a.p + lev) : a.p[off3(a, c, lev)]);
 }
 
-// Returns false when the column needs the EXACT path (pressure not strictly decreasing /
-// given heights not strictly increasing).  HG: heights are given (a.aglh, a.aglhs) instead of
-// being integrated from p, t, td — the reference's separate srh.srh call (srh.py:4).
-// The EXACT instantiation is kept out of line so that its 26 sample registers and second height
-// pass do not inflate the register count (and lower the occupancy) of the streaming path.
-template <class T, bool P1D, bool EXACT, bool HG, bool FH = false>
-__device__ __forceinline__ bool srh_column(const SrhArgs<T>& a, int64_t c, int ks, SrhOut& o) {
-  const int n3 = a.nlev - ks + 1;                 // 3-D levels used
-  double Tvp = 0.0, Pp = 0.0, lnPp = 0.0, Hp;
-  if (HG) {
-    Hp = (double)a.aglhs[c];
-  } else {
-    const double Ps = (double)a.ps[c];
-    Tvp = FH ? (double)tvirt_f((float)a.ts[c], (float)a.tds[c], (float)Ps) : tvirt((double)a.ts[c], (double)a.tds[c], Ps);
-    Hp = a.aglh0; Pp = Ps; lnPp = FH ? 0.0 : spec_log_d(Ps);
-  }
-  const double Hs = Hp;
-  double up = (double)a.us[c], vp = (double)a.vs[c];
-  float upf = (float)a.us[c], vpf = (float)a.vs[c], zpf = (float)Hp;
-
-  // Bunkers samples: index 0 = surface wind, 1..12 = 500 m .. 6000 m
+// Per-column state of the streaming pass.  EXACT: literal DINTERP2DZ search (all 13 samples kept,
+// later brackets overwrite); HG: heights given; FH: binary32 height chain.
+template <bool EXACT, bool HG, bool FH>
+struct SrhState {
+  double Tvp, Pp, lnPp, Hp, Hs, up, vp, S1, S2, S3;
+  float upf, vpf, zpf, s1u, s1v, s2u, s2v, s12u, s12v, s13u, s13v, mu, mv;
   float su[EXACT ? 13 : 1], sv[EXACT ? 13 : 1];
-  float s1u = upf, s1v = vpf, s2u = -999999.0f, s2v = -999999.0f, s12u = -999999.0f, s12v = -999999.0f,
-        s13u = -999999.0f, s13v = -999999.0f;
-  float mu = 0.0f + upf, mv = 0.0f + vpf;         // running in-order sum (fast path)
-  int j = 1;                                      // next sample to find (fast path)
-  if (EXACT) {
-    su[0] = upf; sv[0] = vpf;
-    for (int i = 1; i < 13; ++i) { su[i] = -999999.0f; sv[i] = -999999.0f; }
-  }
-  bool descending = false;
-  if (EXACT) {
-    // DINTERP2DZ orientation test Z(1) > Z(NZ) needs the top height first (f90:211-216)
-    double H = Hp, Tv0 = Tvp, lnP0 = FH ? Pp : lnPp;
+  int j;
+  bool found_top, mono, descending;
+
+  // surface level: (ps, ts, tds) or the given surface height, and the 10 m wind
+  __device__ __forceinline__ void init(double Ps, double Ts, double Tds, double hs_given, double aglh0, double us, double vs,
+                                       float usf, float vsf) {
+    Tvp = 0.0; Pp = 0.0; lnPp = 0.0;
     if (HG) {
-      H = (double)a.aglh[(int64_t)(ks - 1 + n3 - 1) * a.ld + c];
+      Hp = hs_given;
     } else {
-      for (int i = 0; i < n3; ++i) {
-        const int lev = ks - 1 + i;
-        const int64_t off = (int64_t)lev * a.ld + c;
-        const double P = ld_p<T, P1D>(a, c, lev);
-        if (FH) {
-          const float Tvf = tvirt_f((float)a.t[off], (float)a.td[off], (float)P);
-          H = hyps_step_f(H, Tvf, (float)Tv0, (float)P, (float)lnP0);      // lnP0 carries the previous P here
-          Tv0 = Tvf; lnP0 = P;
-        } else {
-          const double Tv = tvirt((double)a.t[off], (double)a.td[off], P);
-          const double lnP = spec_log_d(P);
-          H = hyps_step(H, Tv, Tv0, lnP, lnP0);
-          Tv0 = Tv; lnP0 = lnP;
-        }
-      }
+      Tvp = FH ? (double)tvirt_f((float)Ts, (float)Tds, (float)Ps) : tvirt(Ts, Tds, Ps);
+      Hp = aglh0; Pp = Ps; lnPp = FH ? 0.0 : spec_log_d(Ps);
     }
-    descending = ((float)Hs > (float)H);
+    Hs = Hp;
+    up = us; vp = vs; upf = usf; vpf = vsf; zpf = (float)Hp;
+    s1u = upf; s1v = vpf;
+    s2u = s2v = s12u = s12v = s13u = s13v = -999999.0f;
+    mu = 0.0f + upf; mv = 0.0f + vpf;          // running in-order sum (streaming path)
+    j = 1;
+    if (EXACT) {
+      su[0] = upf; sv[0] = vpf;
+      for (int i = 1; i < 13; ++i) { su[i] = -999999.0f; sv[i] = -999999.0f; }
+    }
+    found_top = false; mono = true; descending = false;
+    S1 = S2 = S3 = 0.0;
   }
 
-  bool found_top = false;
-  double S1 = 0.0, S2 = 0.0, S3 = 0.0;
-  bool mono = true;
-  int i = 0;
-  for (; i < n3; ++i) {
-    const int lev = ks - 1 + i;
-    const int64_t off = (int64_t)lev * a.ld + c;
-    const T uin = a.u[off], vin = a.v[off];
-    double P = 0.0, Tv = 0.0, lnP = 0.0, H;
+  __device__ __forceinline__ bool math_done() const { return !EXACT && found_top && j >= 13; }
+
+  // levels above max(6 km, depth): only the monotonicity of pressure (heights) is checked
+  __device__ __forceinline__ void tail(double PorH) {
+    if (HG) { if (!(PorH > Hp)) mono = false; Hp = PorH; }
+    else { if (!(PorH < Pp)) mono = false; Pp = PorH; }
+  }
+
+  // one level: PorH = pressure (hPa) or the given height; t, td in degC; winds in both precisions
+  __device__ __forceinline__ void step(double PorH, double Tk, double Tdk, double uk, double vk, float ukf, float vkf,
+                                       double depth) {
+    double Tv = 0.0, lnP = 0.0, H;
     if (HG) {
-      H = (double)a.aglh[off];
+      H = PorH;
       if (!(H > Hp)) mono = false;
     } else {
-      P = ld_p<T, P1D>(a, c, lev);
+      const double P = PorH;
       if (!(P < Pp)) mono = false;
       if (FH) {
-        Tv = (double)tvirt_f((float)a.t[off], (float)a.td[off], (float)P);
+        Tv = (double)tvirt_f((float)Tk, (float)Tdk, (float)P);
         H = hyps_step_f(Hp, (float)Tv, (float)Tvp, (float)P, (float)Pp);
       } else {
-        Tv = tvirt((double)a.t[off], (double)a.td[off], P);
+        Tv = tvirt(Tk, Tdk, P);
         lnP = spec_log_d(P);
         H = hyps_step(Hp, Tv, Tvp, lnP, lnPp);                  // stdheight_2D_model_lev.f90:143,152
       }
+      Pp = P;
     }
-    const double uk = (double)uin, vk = (double)vin;
-    const float ukf = (float)uin, vkf = (float)vin, zkf = (float)H;
+    const float zkf = (float)H;
 
-    // ---- Bunkers samples (DINTERP2DZ, f90:188-236) ----
+    // ---- Bunkers samples (DINTERP2DZ, Bunkers_model_lev.f90:188-236) ----
     if (EXACT) {
       const float zlo = descending ? zkf : zpf, zhi = descending ? zpf : zkf;
       const float vlo_u = descending ? ukf : upf, vhi_u = descending ? upf : ukf;
       const float vlo_v = descending ? vkf : vpf, vhi_v = descending ? vpf : vkf;
-      for (int s = 1; s < 13; ++s) {               // later (higher) brackets overwrite: == first hit of the top-down search
-        const float h = 500.0f * (float)s;
+      for (int q = 1; q < 13; ++q) {               // later (higher) brackets overwrite: == first hit of the top-down search
+        const float h = 500.0f * (float)q;
         if (zlo <= h && zhi > h) {
           const float w2 = (h - zlo) / (zhi - zlo);
           const float w1 = (float)(1.0 - (double)w2);
-          su[s] = w1 * vlo_u + w2 * vhi_u;
-          sv[s] = w1 * vlo_v + w2 * vhi_v;
+          su[q] = w1 * vlo_u + w2 * vhi_u;
+          sv[q] = w1 * vlo_v + w2 * vhi_v;
         }
       }
     } else {
@@ -249,51 +238,77 @@ __device__ __forceinline__ bool srh_column(const SrhArgs<T>& a, int64_t c, int k
     // ---- SRH partial sums (DCALRELHL, SREH_model_lev.f90:86-114) ----
     if (!found_top) {
       double ue = uk, ve = vk;
-      if (H > a.depth) {
+      if (H > depth) {
         found_top = true;
-        ue = interp1(uk, up, H, a.depth, Hp);
-        ve = interp1(vk, vp, H, a.depth, Hp);
+        ue = interp1(uk, up, H, depth, Hp);
+        ve = interp1(vk, vp, H, depth, Hp);
       }
       const double du = ue - up, dv = ve - vp;
       S1 = S1 + (ue * dv - ve * du);
       S2 = S2 + dv;
       S3 = S3 + du;
     }
+    Hp = H; Tvp = Tv; lnPp = lnP; up = uk; vp = vk; upf = ukf; vpf = vkf; zpf = zkf;
+  }
 
-    Hp = H; Tvp = Tv; Pp = P; lnPp = lnP; up = uk; vp = vk; upf = ukf; vpf = vkf; zpf = zkf;
-    if (!EXACT && found_top && j >= 13) { ++i; break; }   // nothing above can matter if p keeps decreasing
+  // returns false if the column must be redone by the EXACT path
+  __device__ __forceinline__ bool finish(SrhOut& o) {
+    if (!EXACT) {
+      if (!mono) return false;
+      for (; j < 13; ++j) { mu = mu + -999999.0f; mv = mv + -999999.0f; }   // column top below the sample: VMSG enters the mean
+    } else {
+      mu = 0.0f; mv = 0.0f;
+      for (int q = 0; q < 13; ++q) { mu = mu + su[q]; mv = mv + sv[q]; }
+      s1u = su[0]; s1v = sv[0]; s2u = su[1]; s2v = sv[1];
+      s12u = su[11]; s12v = sv[11]; s13u = su[12]; s13v = sv[12];
+    }
+    bunkers_finish(mu, mv, s1u, s1v, s2u, s2v, s12u, s12v, s13u, s13v, o);
+    if (found_top) {
+      o.srm = -(S1 - (double)o.rmu * S2 + (double)o.rmv * S3);
+      o.slm = -(S1 - (double)o.lmu * S2 + (double)o.lmv * S3);
+    } else {
+      o.srm = 0.0; o.slm = 0.0;                    // ktop == 0: empty sum (SREH_model_lev.f90:97-103)
+    }
+    return true;
   }
-  if (!EXACT) {
-    for (; i < n3; ++i) {                          // monotonicity check only: loads, no math
-      if (HG) {
-        const double H = (double)a.aglh[(int64_t)(ks - 1 + i) * a.ld + c];
-        if (!(H > Hp)) mono = false;
-        Hp = H;
-      } else {
-        const double P = ld_p<T, P1D>(a, c, ks - 1 + i);
-        if (!(P < Pp)) mono = false;
-        Pp = P;
+};
+
+// Per-thread driver over global memory (level-major: coalesced; level-last: strided, EXACT kernel only).
+// Returns false when the column needs the EXACT path.
+template <class T, bool P1D, bool EXACT, bool HG, bool FH = false>
+__device__ __forceinline__ bool srh_column(const SrhArgs<T>& a, int64_t c, int ks, SrhOut& o) {
+  const int n3 = a.nlev - ks + 1;                 // 3-D levels used
+  SrhState<EXACT, HG, FH> st;
+  st.init(HG ? 0.0 : (double)a.ps[c], HG ? 0.0 : (double)a.ts[c], HG ? 0.0 : (double)a.tds[c],
+          HG ? (double)a.aglhs[c] : 0.0, a.aglh0, (double)a.us[c], (double)a.vs[c], (float)a.us[c], (float)a.vs[c]);
+  if (EXACT) {
+    // DINTERP2DZ orientation test Z(1) > Z(NZ) needs the top height first (f90:211-216)
+    double H;
+    if (HG) {
+      H = (double)a.aglh[off3(a, c, ks - 1 + n3 - 1)];
+    } else {
+      SrhState<false, false, FH> pre;
+      pre.init((double)a.ps[c], (double)a.ts[c], (double)a.tds[c], 0.0, a.aglh0, 0.0, 0.0, 0.0f, 0.0f);
+      for (int i = 0; i < n3; ++i) {
+        const int64_t off = off3(a, c, ks - 1 + i);
+        pre.step(ld_p<T, P1D>(a, c, ks - 1 + i), (double)a.t[off], (double)a.td[off], 0.0, 0.0, 0.0f, 0.0f, 1e300);
       }
+      H = pre.Hp;
     }
-    if (!mono) return false;
-    for (; j < 13; ++j) {                          // column top below the sample height: VMSG enters the mean
-      mu = mu + -999999.0f; mv = mv + -999999.0f;
-      // s2/s12/s13 keep their VMSG initial values
-    }
-  } else {
-    mu = 0.0f; mv = 0.0f;
-    for (int s = 0; s < 13; ++s) { mu = mu + su[s]; mv = mv + sv[s]; }
-    s1u = su[0]; s1v = sv[0]; s2u = su[1]; s2v = sv[1];
-    s12u = su[11]; s12v = sv[11]; s13u = su[12]; s13v = sv[12];
+    st.descending = ((float)st.Hs > (float)H);
   }
-  bunkers_finish(mu, mv, s1u, s1v, s2u, s2v, s12u, s12v, s13u, s13v, o);
-  if (found_top) {
-    o.srm = -(S1 - (double)o.rmu * S2 + (double)o.rmv * S3);
-    o.slm = -(S1 - (double)o.lmu * S2 + (double)o.lmv * S3);
-  } else {
-    o.srm = 0.0; o.slm = 0.0;                      // ktop == 0: empty sum (SREH_model_lev.f90:97-103)
+  int i = 0;
+  for (; i < n3; ++i) {
+    const int lev = ks - 1 + i;
+    const int64_t off = off3(a, c, lev);
+    const T uin = a.u[off], vin = a.v[off];
+    if (HG) st.step((double)a.aglh[off], 0.0, 0.0, (double)uin, (double)vin, (float)uin, (float)vin, a.depth);
+    else st.step(ld_p<T, P1D>(a, c, lev), (double)a.t[off], (double)a.td[off], (double)uin, (double)vin, (float)uin, (float)vin, a.depth);
+    if (st.math_done()) { ++i; break; }            // nothing above can matter if p keeps decreasing
   }
-  return true;
+  if (!EXACT)
+    for (; i < n3; ++i) st.tail(HG ? (double)a.aglh[off3(a, c, ks - 1 + i)] : ld_p<T, P1D>(a, c, ks - 1 + i));
+  return st.finish(o);
 }
 
 template <class T>
@@ -304,9 +319,9 @@ __device__ __forceinline__ void srh_store(const SrhArgs<T>& a, int64_t c, const 
   if (a.mean6) { a.mean6[2 * c] = o.m6u; a.mean6[2 * c + 1] = o.m6v; }
 }
 
-// Streaming pass.  Columns that need the literal DINTERP2DZ search (non-monotone pressure /
-// heights) are appended to a work list and left to srh_exact_kernel, so that the EXACT code's
-// registers (13 + 13 samples, second height pass) never limit this kernel's occupancy.
+// Streaming pass over level-major input.  Columns that need the literal DINTERP2DZ search
+// (non-monotone pressure / heights) are appended to a work list and left to srh_exact_kernel, so
+// that the EXACT code's registers (13 + 13 samples, second height pass) never limit this kernel.
 template <class T, bool P1D, bool HG, bool FH>
 __global__ void __launch_bounds__(128) srh_kernel(const SrhArgs<T> a) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -315,6 +330,80 @@ __global__ void __launch_bounds__(128) srh_kernel(const SrhArgs<T> a) {
   ks = ks < 1 ? 1 : (ks > a.nlev ? a.nlev : ks);
   SrhOut o;
   if (srh_column<T, P1D, false, HG, FH>(a, c, ks, o)) srh_store(a, c, o);
+  else a.work_list[atomicAdd(a.work_count, 1)] = (int32_t)c;
+}
+
+// Streaming pass over the REFERENCE layout (level last, each column contiguous; core.py:44-50) with no
+// relayout pass: a warp owns 32 consecutive columns and pulls them through shared memory KL levels at
+// a time — each load instruction reads KL consecutive levels (one or two 32-byte sectors) of 32/KL
+// columns, the tile is stored [field][level][column] and every lane then walks its own column.  All
+// lanes of a warp stay in the loop (loads are cooperative); a lane that has passed max(6 km, depth)
+// stops doing math, and once every lane has, only pressure is fetched for the monotonicity check.
+template <class T, bool P1D, bool FH>
+__global__ void __launch_bounds__(128) srh_tiled_kernel(const SrhArgs<T> a) {
+  constexpr int KL = 8;                              // levels per tile (8 x 4 B = one 32-byte sector per column)
+  constexpr int NF = P1D ? 4 : 5;                    // t, td, u, v [, p]
+  __shared__ T tile[4][NF][KL][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t c0 = (int64_t)blockIdx.x * blockDim.x + warp * 32;     // first column of this warp
+  if (c0 >= a.ncol) return;                          // whole warp out of range (warp-uniform)
+  const int64_t c = c0 + lane;
+  const bool valid = c < a.ncol;
+  int ks = (valid && a.start) ? a.start[c] : 1;
+  ks = ks < 1 ? 1 : (ks > a.nlev ? a.nlev : ks);
+  const int n3 = valid ? a.nlev - ks + 1 : 0;
+  int n3max = n3;
+  for (int d = 16; d; d >>= 1) n3max = max(n3max, __shfl_xor_sync(0xffffffffu, n3max, d));
+
+  SrhState<false, false, FH> st;
+  if (valid) st.init((double)a.ps[c], (double)a.ts[c], (double)a.tds[c], 0.0, a.aglh0, (double)a.us[c], (double)a.vs[c],
+                     (float)a.us[c], (float)a.vs[c]);
+  int phase = valid ? 0 : 2;                         // 0 = math, 1 = monotonicity tail, 2 = finished
+  const T* fld[5] = {a.t, a.td, a.u, a.v, a.p};
+
+  for (int k0 = 0; k0 < n3max; k0 += KL) {
+    const bool any_math = __any_sync(0xffffffffu, phase == 0);
+    if (!any_math && P1D) break;                     // the tail of a pressure grid needs no 3-D field
+    // ---- cooperative tile load: lane -> (column jj = it*(32/KL) + lane/KL, level e = lane%KL) ----
+    const int f0 = any_math ? 0 : 4, f1 = any_math ? NF : 5;
+    for (int it = 0; it < KL; ++it) {
+      const int jj = it * (32 / KL) + lane / KL, e = lane % KL;
+      const int ks_j = __shfl_sync(0xffffffffu, ks, jj), n3_j = __shfl_sync(0xffffffffu, n3, jj);
+      if (k0 + e < n3_j) {
+        const int64_t src = (c0 + jj) * (int64_t)a.nlev + (ks_j - 1 + k0 + e);
+        for (int f = f0; f < f1; ++f) tile[warp][f == 4 ? NF - 1 : f][e][jj] = fld[f][src];
+      }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int e = 0; e < KL; ++e) {
+      const int i = k0 + e;
+      if (i >= n3 || phase == 2) break;
+      const double P = P1D ? (double)__ldg(a.p + (ks - 1 + i)) : (double)tile[warp][NF - 1][e][lane];
+      if (phase == 0) {
+        const T uin = tile[warp][2][e][lane], vin = tile[warp][3][e][lane];
+        st.step(P, (double)tile[warp][0][e][lane], (double)tile[warp][1][e][lane], (double)uin, (double)vin, (float)uin,
+                (float)vin, a.depth);
+        if (st.math_done()) phase = 1;
+      } else {
+        st.tail(P);
+      }
+      if (i + 1 >= n3) phase = 2;
+    }
+    __syncwarp();
+  }
+  if (!valid) return;
+  SrhOut o;
+  if (P1D && phase != 2) {
+    // Pressure grid whose warp left the tile loop early: the levels not yet visited only matter for the
+    // monotonicity check, and they live in the shared 1-D axis.  Re-checking ALL used levels is
+    // equivalent (the visited ones were checked already) and costs nlev loads from the read-only path.
+    double pp = (double)a.ps[c];
+    bool mono = true;
+    for (int i = 0; i < n3; ++i) { const double P = (double)__ldg(a.p + (ks - 1 + i)); if (!(P < pp)) mono = false; pp = P; }
+    st.mono = st.mono && mono;
+  }
+  if (st.finish(o)) srh_store(a, c, o);
   else a.work_list[atomicAdd(a.work_count, 1)] = (int32_t)c;
 }
 
