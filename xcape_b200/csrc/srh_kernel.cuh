@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(128) srh_kernel(const SrhArgs<T> a) {
 // lanes of a warp stay in the loop (loads are cooperative); a lane that has passed max(6 km, depth)
 // stops doing math, and once every lane has, only pressure is fetched for the monotonicity check.
 template <class T, bool P1D, bool FH>
-__global__ void __launch_bounds__(128) srh_tiled_kernel(const SrhArgs<T> a) {
+__global__ void __launch_bounds__(128, 7) srh_tiled_kernel(const SrhArgs<T> a) {
   constexpr int KL = 8;                              // levels per tile (8 x 4 B = one 32-byte sector per column)
   constexpr int NF = P1D ? 4 : 5;                    // t, td, u, v [, p]
   __shared__ T tile[4][NF][KL][33];
@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(128) srh_tiled_kernel(const SrhArgs<T> a) {
     if (!any_math && P1D) break;                     // the tail of a pressure grid needs no 3-D field
     // ---- cooperative tile load: lane -> (column jj = it*(32/KL) + lane/KL, level e = lane%KL) ----
     const int f0 = any_math ? 0 : 4, f1 = any_math ? NF : 5;
+#pragma unroll 2
     for (int it = 0; it < KL; ++it) {
       const int jj = it * (32 / KL) + lane / KL, e = lane % KL;
       const int ks_j = __shfl_sync(0xffffffffu, ks, jj), n3_j = __shfl_sync(0xffffffffu, n3, jj);
