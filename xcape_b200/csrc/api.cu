@@ -185,11 +185,7 @@ int srh_device_t(const void* p, const void* t, const void* td, const void* u, co
   int rc;
   const void* q;
   int64_t ld = ncol, l2 = ncol;
-  if (layout == XCAPE_LEVEL_LAST) {
-    // reference layout: no relayout pass — srh_tiled_kernel reads it through shared-memory tiles
-    a.t = (const T*)t; a.td = (const T*)td; a.u = (const T*)u; a.v = (const T*)v; a.p = (const T*)p;
-    a.lev_stride = 1; a.col_stride = nlev;
-  } else {
+  {
     if ((rc = canon3d_same(t, dtype, layout, ncol, nlev, ld_in, sc, &q, &ld, s))) return rc; a.t = (const T*)q;
     if ((rc = canon3d_same(td, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.td = (const T*)q;
     if ((rc = canon3d_same(u, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.u = (const T*)q;

@@ -16,15 +16,7 @@ int launch_srh_t(const SrhArgs<T>& a, bool p1d, cudaStream_t s) {
   if (a.ncol >= (int64_t)1 << 31) return fail(XCAPE_ERR_ARG, "srh: more than 2^31-1 columns per call");
   XC_CUDA(cudaMemsetAsync(a.work_count, 0, sizeof(int), s));
   const bool fh = a.fast_heights != 0;
-  const bool tiled = (a.col_stride != 1);            // reference layout, read through shared-memory tiles
-  if (tiled && a.aglh) return fail(XCAPE_ERR_ARG, "internal: heights-given SRH expects level-major fields");
-  if (tiled) {
-    if (p1d && fh) srh_tiled_kernel<T, true, true><<<blocks, 128, 0, s>>>(a);
-    else if (p1d) srh_tiled_kernel<T, true, false><<<blocks, 128, 0, s>>>(a);
-    else if (fh) srh_tiled_kernel<T, false, true><<<blocks, 128, 0, s>>>(a);
-    else srh_tiled_kernel<T, false, false><<<blocks, 128, 0, s>>>(a);
-  }
-  else if (a.aglh) srh_kernel<T, false, true, false><<<blocks, 128, 0, s>>>(a);
+  if (a.aglh) srh_kernel<T, false, true, false><<<blocks, 128, 0, s>>>(a);
   else if (p1d && fh) srh_kernel<T, true, false, true><<<blocks, 128, 0, s>>>(a);
   else if (p1d) srh_kernel<T, true, false, false><<<blocks, 128, 0, s>>>(a);
   else if (fh) srh_kernel<T, false, false, true><<<blocks, 128, 0, s>>>(a);
