@@ -146,6 +146,10 @@ XCAPE_API const char* xcape_cuda_last_error(void);      /* thread-local message 
 XCAPE_API int xcape_cuda_device_count(void);            /* < 0 on error */
 XCAPE_API const char* xcape_cuda_version(void);         /* "xcape_b200 <semver> sm_100a" */
 XCAPE_API int64_t xcape_cuda_kernel_launches(void);     /* kernels launched by this library so far (process-wide) */
+/* The library keeps its stream-ordered scratch (relayout buffers, staging blocks) in a private
+ * cudaMemPool per device and never returns it to the driver on its own (re-mapping ~300 MB per call cost
+ * 5 ms per ERA5 field).  This call synchronises `device` and hands the cached memory back. */
+XCAPE_API int xcape_cuda_release_memory(int device);
 /* Measured arithmetic peaks of `device` (roofline denominators the driver's MEASURED_PEAKS.json
  * lacks): dependent-chain-free FFMA / DFMA loops, 2 flop per FMA, best of `reps` launches. */
 XCAPE_API int xcape_cuda_measure_peaks(int device, int reps, double* fp32_tflops, double* fp64_tflops);

@@ -654,3 +654,18 @@ def test_full_size_configs_properties(core, cfg):
     lo, hi = f([d[k][:h] for k in keys]), f([d[k][h:] for k in keys])
     for a, b, c in zip(lo, hi, full):
         assert np.array_equal(np.concatenate([a, b]), c)
+
+
+def test_release_memory(core):
+    """xcape_cuda_release_memory hands the cached scratch pool back; the next call simply re-grows it."""
+    import torch
+    from xcape_b200 import _lib
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C2', cols=(0, 300_000))
+    args = (d['p'], d['t'], d['td'], d['ps'], d['ts'], d['tds'])
+    a = core.calc_cape(*args, vertical_lev='pressure', method='cuda')
+    used = torch.cuda.mem_get_info()[0]
+    _lib.release_memory(0)
+    assert torch.cuda.mem_get_info()[0] >= used
+    b = core.calc_cape(*args, vertical_lev='pressure', method='cuda')
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))

@@ -20,7 +20,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_NODEV = 0, 1, 2, 3
 # every symbol include/xcape_b200.h declares (tests check the library exports all of them)
 SYMBOLS = ('xcape_cuda_cape', 'xcape_cuda_srh', 'xcape_cuda_srh_from_heights', 'xcape_cuda_stdheight', 'xcape_cuda_pres_lev_pos',
            'xcape_cuda_last_error', 'xcape_cuda_device_count', 'xcape_cuda_version',
-           'xcape_cuda_kernel_launches', 'xcape_cuda_measure_peaks')
+           'xcape_cuda_kernel_launches', 'xcape_cuda_measure_peaks', 'xcape_cuda_release_memory')
 
 _lib = None
 
@@ -61,6 +61,8 @@ def lib():
         L.xcape_cuda_version.restype = C.c_char_p
         L.xcape_cuda_device_count.restype = i32
         L.xcape_cuda_kernel_launches.restype = i64
+        L.xcape_cuda_release_memory.restype = i32
+        L.xcape_cuda_release_memory.argtypes = [i32]
         L.xcape_cuda_measure_peaks.restype = i32
         L.xcape_cuda_measure_peaks.argtypes = [i32, i32, C.POINTER(f64), C.POINTER(f64)]
         _lib = L
@@ -84,6 +86,11 @@ def measure_peaks(device=0, reps=5):
     a, b = C.c_double(0.0), C.c_double(0.0)
     check(lib().xcape_cuda_measure_peaks(int(device), int(reps), C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def release_memory(device=0):
+    """Return the library's cached device scratch on ``device`` to the CUDA driver."""
+    check(lib().xcape_cuda_release_memory(int(device)))
 
 
 def device_count():

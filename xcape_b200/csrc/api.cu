@@ -522,6 +522,14 @@ int xcape_cuda_device_count(void) {
   return n;
 }
 
+int xcape_cuda_release_memory(int device) {
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(XCAPE_ERR_NODEV, "cudaSetDevice failed");
+  XC_CUDA(cudaDeviceSynchronize());
+  if (cudaMemPool_t pool = pool_for_current_device()) XC_CUDA(cudaMemPoolTrimTo(pool, 0));
+  return XCAPE_OK;
+}
+
 int xcape_cuda_measure_peaks(int device, int reps, double* fp32_tflops, double* fp64_tflops) {
   DeviceGuard dg(device);
   if (!dg.ok) return fail(XCAPE_ERR_NODEV, "cudaSetDevice failed");
