@@ -379,8 +379,21 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
                const std::vector<HostIn1>& in1, const std::vector<HostOut>& outs, F launch) {
   const int64_t chunk = std::min<int64_t>(ncol, chunk_cols());          // capacity of a slot
   const int64_t first = std::min<int64_t>(chunk, first_chunk_cols());
-  int nblocks = 0;
-  for (int64_t c = 0, n = first; c < ncol; c += n, n = std::min<int64_t>(chunk, n * 2)) ++nblocks;
+  // block plan: geometric ramp, then full blocks; a short remainder is shared with its predecessor so that
+  // the call does not end on a kernel too small to fill the GPU
+  std::vector<int64_t> plan;
+  for (int64_t c = 0, n = first; c < ncol; n = std::min<int64_t>(chunk, n * 2)) {
+    const int64_t m = std::min<int64_t>(n, ncol - c);
+    plan.push_back(m);
+    c += m;
+  }
+  if (plan.size() >= 2 && plan.back() * 2 < plan[plan.size() - 2]) {
+    const int64_t tot = plan.back() + plan[plan.size() - 2];
+    const int64_t a = ((tot / 2 + 127) / 128) * 128;
+    plan[plan.size() - 2] = a;
+    plan.back() = tot - a;
+  }
+  const int nblocks = (int)plan.size();
   const int nstream = std::min<int>(ring_streams(), nblocks);
   cudaStream_t st[kMaxStreams] = {};
   cudaEvent_t done[kMaxStreams] = {};
@@ -445,10 +458,9 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
     }
     if (trace) fprintf(stderr, "[xcape_b200]   setup done at %.3f ms\n", now() - t_begin);
     int i = 0;
-    int64_t want = first;
-    for (int64_t c0 = 0; c0 < ncol; i = (i + 1) % nstream) {
-      const int64_t n = std::min<int64_t>(want, ncol - c0);
-      want = std::min<int64_t>(chunk, want * 2);
+    int64_t c0 = 0;
+    for (size_t blk = 0; blk < plan.size(); ++blk, i = (i + 1) % nstream) {
+      const int64_t n = plan[blk];
       cudaStream_t s = st[i];
       int r = drain(i);                            // slot reuse: its previous block must have left
       if (r) return r;
