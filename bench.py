@@ -201,9 +201,11 @@ class CapeWorkload:
     def roofline(self, ms_kernel, st, fp32_peak, fp64_peak, hbm_peak, hbm_src):
         tf = FLOP_PER_ITER * st['total_iter'] / (ms_kernel * 1e-3) / 1e12
         gbs = self.bytes_per_col * self.ncol / (ms_kernel * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(f'cape_{self.cfg}_{self.precision}', self.ncol)
         return {
             'bound': 'fp32', 'achieved': tf, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': tf / fp32_peak,
-            'traffic': ncu_traffic(f'cape_{self.cfg}_{self.precision}', self.ncol),
+            'traffic': traffic, 'traffic_unit': 'DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, scaled by columns)',
+            'traffic_source': traffic_src,
             'kernel': f'cape_kernel<MathSpec,{self.src_id},1,{str(self.p1d).lower()}>', 'kernel_ms': ms_kernel,
             'work': f"{FLOP_PER_ITER:.0f} flop x {st['total_iter'] / self.ncol:.1f} moist iterations/column of the reference algorithm "
                     f"(= the faithful kernel's count); this kernel executed {st['executed_iter'] / self.ncol:.1f}/column",
@@ -282,8 +284,9 @@ class SrhWorkload:
 
     def roofline(self, ms_kernel, st, fp32_peak, fp64_peak, hbm_peak, hbm_src):
         gbs = self.bytes_per_col * self.ncol / (ms_kernel * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic('srh_' + self.cfg, self.ncol)
         return {'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
-                'traffic': ncu_traffic('srh_' + self.cfg, self.ncol),
+                'traffic': traffic, 'traffic_source': traffic_src,
                 'kernel': 'srh_kernel<float,false,false> (+ srh_exact_kernel on an empty work list)', 'kernel_ms': ms_kernel, 'bytes_per_column': self.bytes_per_col,
                 'peak_source': hbm_src, 'fp64_peak_tflops': fp64_peak,
                 'note': 'faithful: hypsometric exp/log chain in binary64 (reference arithmetic); fast: binary32'}
@@ -293,10 +296,9 @@ def ncu_traffic(key, ncol):
     """DRAM bytes per launch from the committed ncu capture of the same kernel (profiles/ncu_traffic.json)."""
     try:
         t = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))[key]
-        return {'bytes_per_launch': t['dram_bytes_per_column'] * ncol, 'bytes_per_column': t['dram_bytes_per_column'],
-                'source': t['source']}
+        return t['dram_bytes_per_column'] * ncol, t['source']
     except (OSError, KeyError, ValueError):
-        return None
+        return None, None
 
 
 def get_workload(name):
