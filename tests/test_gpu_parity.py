@@ -669,3 +669,29 @@ def test_release_memory(core):
     assert torch.cuda.mem_get_info()[0] >= used
     b = core.calc_cape(*args, vertical_lev='pressure', method='cuda')
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_host_ring_level_major_and_float64_across_blocks(core):
+    """Host-pointer path over several ring blocks (32k / 64k / 128k / ... columns) for the layouts and
+    dtypes that take the strided (cudaMemcpy2DAsync) and cast-on-device routes; pinned and pageable."""
+    import torch
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C2', cols=(0, 300_000 + 13))
+    kw = dict(source='most-unstable', pinc=500., vertical_lev='pressure', method='cuda')
+    base = core.calc_cape(d['p'], d['t'], d['td'], d['ps'], d['ts'], d['tds'], **kw)
+    tm, tdm = np.ascontiguousarray(d['t'].T), np.ascontiguousarray(d['td'].T)
+    lm = core.calc_cape(d['p'], tm, tdm, d['ps'], d['ts'], d['tds'], lev_axis=0, **kw)
+    assert_bitexact(lm, base, 'level-major host, multi-block')
+    lm64 = core.calc_cape(d['p'].astype(np.float64), tm.astype(np.float64), tdm.astype(np.float64),
+                          d['ps'].astype(np.float64), d['ts'].astype(np.float64), d['tds'].astype(np.float64), lev_axis=0, **kw)
+    assert_bitexact(lm64, base, 'level-major float64 host, multi-block')
+    pin = {k: torch.from_numpy(d[k]).pin_memory() for k in ('t', 'td', 'ps', 'ts', 'tds')}
+    pinned = core.calc_cape(d['p'], *(pin[k].numpy() for k in ('t', 'td', 'ps', 'ts', 'tds')), **kw)
+    assert_bitexact(pinned, base, 'pinned host inputs')
+    srh_keys = ('p', 't', 'td', 'u', 'v', 'ps', 'ts', 'tds', 'us', 'vs')
+    d3 = make_soundings('C3', cols=(0, 150_000 + 5))
+    s_base = core.calc_srh(*(d3[k] for k in srh_keys), vertical_lev='sigma', output_var='all', method='cuda')
+    s_lm = core.calc_srh(*(np.ascontiguousarray(d3[k].T) for k in srh_keys[:5]), *(d3[k] for k in srh_keys[5:]),
+                         vertical_lev='sigma', output_var='all', method='cuda', lev_axis=0)
+    for a, b in zip(s_lm, s_base):
+        assert np.array_equal(a, b)
