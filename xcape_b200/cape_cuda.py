@@ -124,17 +124,6 @@ def pres_lev_pos(p_1d, p_s, *, device=0, stream=None):
     """Device version of core.py:286-289: 1-based index of the first level with p <= ps
     (1 when every level lies below the surface), evaluated in the inputs' dtype."""
     L = _lib.lib()
-    _, f1, p, dt, _, mem, _ = _prep_plp(p_1d, p_s)
-    ps_ = f1[0]
-    n = ps_.shape[0]
-    out = A.empty_like_host_or_device(ps_, (n,), 'int32')
-    rc = L.xcape_cuda_pres_lev_pos(A.ptr(p), A.ptr(ps_), C.c_int64(n), int(p.shape[0]), dt, mem, A.ptr(out),
-                                   A.device_of(ps_, device), A.stream_of(ps_, stream))
-    _lib.check(rc)
-    return out
-
-
-def _prep_plp(p_1d, p_s):
     on_dev = [A.is_cuda(p_1d), A.is_cuda(p_s)]
     if any(on_dev) and not all(on_dev):
         raise ValueError('inputs must all be host arrays or all CUDA tensors')
@@ -143,5 +132,11 @@ def _prep_plp(p_1d, p_s):
     dt = A.common_dtype([p_1d, p_s])
     p = A.dense_1d(A.cast(p_1d, dt))
     ps_ = A.dense_1d(A.cast(p_s, dt))
-    mem = _lib.MEM_DEVICE if all(on_dev) else _lib.MEM_HOST
-    return None, [ps_], p, (_lib.F32 if dt == 'float32' else _lib.F64), None, mem, ps_
+    n = ps_.shape[0]
+    out = A.empty_like_host_or_device(ps_, (n,), 'int32')
+    rc = L.xcape_cuda_pres_lev_pos(A.ptr(p), A.ptr(ps_), C.c_int64(n), int(p.shape[0]),
+                                   _lib.F32 if dt == 'float32' else _lib.F64,
+                                   _lib.MEM_DEVICE if all(on_dev) else _lib.MEM_HOST, A.ptr(out),
+                                   A.device_of(ps_, device), A.stream_of(ps_, stream))
+    _lib.check(rc)
+    return out
