@@ -36,7 +36,7 @@ using MathPolicy = MathSpec;
 
 template <int SOURCE, int ADIABAT, bool P1D>
 static int launch(const CapeArgs& a, cudaStream_t s) {
-  const int threads = 128;
+  const int threads = XC_CAPE_THREADS;
   const int64_t blocks = (a.ncol + threads - 1) / threads;
   if (blocks <= 0) return XCAPE_OK;
   cape_kernel<MathPolicy, SOURCE, ADIABAT, P1D><<<(unsigned)blocks, threads, 0, s>>>(a);
