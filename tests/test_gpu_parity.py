@@ -441,6 +441,9 @@ def test_devices_kwarg_shards_columns_over_gpus(core):
         assert np.array_equal(a, b)
     other = core.calc_cape(*args, device=n - 1, **kw)          # explicit non-default device
     assert_bitexact(other, one, f'device={n - 1}')
+    lm = core.calc_cape(d['p'], np.ascontiguousarray(d['t'].T), np.ascontiguousarray(d['td'].T), d['ps'], d['ts'], d['tds'],
+                        lev_axis=0, devices=list(range(n)), **kw)      # level-major host arrays, sharded
+    assert_bitexact(lm, one, 'level-major sharded')
 
 
 @pytest.mark.parametrize('precision', ['fast', 'fast-relaxed'])

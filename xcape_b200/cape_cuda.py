@@ -86,18 +86,23 @@ def cape(p_2d, t_2d, td_2d, p_s, t_s, td_s, flag_1d, pres_lev_pos, source, ml_de
         if n <= 0:
             return
 
+        es = 4 if dt == _lib.F32 else 8
+        whole = (c0 == 0 and c1 == ngrid)
+        keep = []                                  # dense per-shard copies of level-major fields stay alive for the call
+
         def off3(a):
-            es = 4 if dt == _lib.F32 else 8
-            base = A.ptr(a)
-            return base + (c0 * nlev * es if layout == _lib.LEVEL_LAST else c0 * es)
+            if layout == _lib.LEVEL_LAST:
+                return A.ptr(a) + c0 * nlev * es
+            if whole:
+                return A.ptr(a)
+            # a column block of a level-major host array is strided: hand the shard over as its own
+            # dense [nlev, n] block (the C ABI takes the block width as the row pitch)
+            keep.append(np.ascontiguousarray(a[:, c0:c1]))
+            return A.ptr(keep[-1])
 
         def off1(a, es):
             return None if a is None else A.ptr(a) + c0 * es
 
-        es = 4 if dt == _lib.F32 else 8
-        whole = (c0 == 0 and c1 == ngrid)
-        if not whole and layout == _lib.LEVEL_MAJOR:
-            raise ValueError('sharding level-major host arrays needs contiguous blocks; pass level-last arrays')
         rc = L.xcape_cuda_cape(
             A.ptr(p) if p_is_1d else off3(p), off3(t_), off3(td_), off1(ps_, es), off1(ts_, es), off1(tds_, es),
             C.c_int64(n), nlev, p_is_1d, dt, layout, mem, int(source), int(adiabat),

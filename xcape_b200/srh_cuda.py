@@ -77,11 +77,16 @@ def srh_fused(p_2d, t_2d, td_2d, u_2d, v_2d, p_s, t_s, td_s, u_s, v_s, flag_1d, 
         n = c1 - c0
         if n <= 0:
             return
-        if not (c0 == 0 and c1 == ngrid) and layout == _lib.LEVEL_MAJOR:
-            raise ValueError('sharding level-major host arrays needs contiguous blocks; pass level-last arrays')
+        whole = (c0 == 0 and c1 == ngrid)
+        keep = []
 
         def off3(a):
-            return A.ptr(a) + (c0 * nlev * es if layout == _lib.LEVEL_LAST else c0 * es)
+            if layout == _lib.LEVEL_LAST:
+                return A.ptr(a) + c0 * nlev * es
+            if whole:
+                return A.ptr(a)
+            keep.append(np.ascontiguousarray(a[:, c0:c1]))     # dense [nlev, n] shard of a level-major host array
+            return A.ptr(keep[-1])
 
         def off1(a, e):
             return None if a is None else A.ptr(a) + c0 * e
