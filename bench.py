@@ -371,6 +371,12 @@ def main():
     if args.impl == 'reference':
         return run_reference(args, rank, world, wl)
 
+    # stdout must carry exactly ONE JSON line: NCCL prints "NCCL version ..." to the C-level stdout when the
+    # first communicator is created, so fd 1 points at stderr until the line is ready.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from xcape_b200 import _lib
@@ -381,7 +387,6 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # stdout carries exactly one JSON line
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():
@@ -569,7 +574,10 @@ def main():
                     'ms_per_step': e2e_s * 1e3, 'matches_device_path': bool(same),
                     'two_host_threads': {'value': world * ncol / e2e2_s, 'ms_per_step': e2e2_s * 1e3}},
             'roofline': roofline, 'cpu_baseline': cpu, 'other_precision': other}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
