@@ -353,14 +353,15 @@ bool is_pageable_host(const void* p) {
   return a.type == cudaMemoryTypeUnregistered;
 }
 
-// Streams and events of the host-path ring are created once per (host thread, device) and kept:
-// cudaStreamCreate costs ~0.1 ms, a visible share of a 3-17 ms call.
-struct RingCache {
+// Streams and events of the host-path ring are created once and recycled through a process-wide pool
+// (cudaStreamCreate costs ~0.1 ms, a visible share of a 3-17 ms call).  A pool rather than thread-local
+// storage: callers such as dask workers or this package's own multi-GPU sharding use short-lived threads,
+// which would otherwise create (and leak) a ring per call.
+struct Ring {
   int dev = -1, n = 0;
   cudaStream_t st[kMaxStreams] = {};
   cudaEvent_t ev[kMaxStreams] = {};
-  int ensure(int device, int want) {
-    if (dev != device) { dev = device; n = 0; }     // handles of another device are simply left alive (tiny)
+  int ensure(int want) {
     for (; n < want; ++n) {
       XC_CUDA(cudaStreamCreateWithFlags(&st[n], cudaStreamNonBlocking));
       XC_CUDA(cudaEventCreateWithFlags(&ev[n], cudaEventDisableTiming));
@@ -368,7 +369,20 @@ struct RingCache {
     return XCAPE_OK;
   }
 };
-thread_local RingCache t_ring;
+struct RingPool {
+  std::mutex mu;
+  std::vector<Ring*> idle;
+  Ring* acquire(int device) {
+    std::lock_guard<std::mutex> lk(mu);
+    for (size_t i = 0; i < idle.size(); ++i)
+      if (idle[i]->dev == device) { Ring* r = idle[i]; idle.erase(idle.begin() + i); return r; }
+    Ring* r = new Ring();
+    r->dev = device;
+    return r;
+  }
+  void release(Ring* r) { std::lock_guard<std::mutex> lk(mu); idle.push_back(r); }
+};
+RingPool g_rings;
 
 // A D2H copy into PAGEABLE memory blocks the host until the producing kernel has finished, which
 // would serialise the ring (r1c probe: one block per field was faster than four).  Per-column
@@ -397,6 +411,7 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
   const int nstream = std::min<int>(ring_streams(), nblocks);
   cudaStream_t st[kMaxStreams] = {};
   cudaEvent_t done[kMaxStreams] = {};
+  Ring* ring = nullptr;
   Block b[kMaxStreams];
   struct Pending { bool on = false; int64_t c0 = 0, n = 0; } pend[kMaxStreams];
   std::vector<void*> stage[kMaxStreams];          // pinned staging per output (nullptr = direct copy)
@@ -425,10 +440,11 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
   auto body = [&]() -> int {
     int cur_dev = 0;
     XC_CUDA(cudaGetDevice(&cur_dev));
-    { int r = t_ring.ensure(cur_dev, nstream); if (r) return r; }
+    ring = g_rings.acquire(cur_dev);
+    { int r = ring->ensure(nstream); if (r) return r; }
     for (int i = 0; i < nstream; ++i) {
-      st[i] = t_ring.st[i];
-      done[i] = t_ring.ev[i];
+      st[i] = ring->st[i];
+      done[i] = ring->ev[i];
       for (size_t k = 0; k < in3.size(); ++k) {
         void* q; XC_CUDA(pool_alloc(&q, (size_t)chunk * nlev * es, st[i])); b[i].in3.push_back(q);
         void* h = nullptr;
@@ -512,6 +528,7 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
     for (void* h : stage3[i]) if (h) g_pinned.release(h);
     for (void* h : stage1[i]) if (h) g_pinned.release(h);
   }
+  if (ring) g_rings.release(ring);
   if (rc) { cudaGetLastError(); g_last_error = keep; }
   if (trace) fprintf(stderr, "[xcape_b200] run_staged ncol=%lld blocks=%d streams=%d: body %.3f ms, teardown %.3f ms\n",
                      (long long)ncol, nblocks, nstream, t_body - t_begin, now() - t_body);
