@@ -698,3 +698,37 @@ def test_host_ring_level_major_and_float64_across_blocks(core):
                          vertical_lev='sigma', output_var='all', method='cuda', lev_axis=0)
     for a, b in zip(s_lm, s_base):
         assert np.array_equal(a, b)
+
+
+def test_stdheight_layouts_and_memory_spaces(oracle_mod):
+    """xcape_cuda_stdheight: level-last / level-major, host / device, float32 / float64 inputs, model and
+    pressure grids (levels below the start level are -999999, stdheight_2D_pressure_lev.f90:85-87)."""
+    import torch
+    from xcape_b200.cape_cuda import pres_lev_pos
+    from xcape_b200.stdheight_cuda import stdheight
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C3', cols=(0, 40_000 + 3))
+    Ho, Hso = oracle_mod.stdheight(d['p'].T, d['t'].T, d['td'].T, d['ps'], d['ts'], d['tds'], 0, 1, 2., 1, nthreads=8)
+    variants = {
+        'level-last host': (d['p'].T, d['t'].T, d['td'].T),
+        'level-major host': tuple(np.ascontiguousarray(d[k].T) for k in ('p', 't', 'td')),
+        'level-major host f64': tuple(np.ascontiguousarray(d[k].T).astype(np.float64) for k in ('p', 't', 'td')),
+    }
+    for name, (p2, t2, td2) in variants.items():
+        H, Hs = stdheight(p2, t2, td2, d['ps'].astype(p2.dtype), d['ts'].astype(p2.dtype), d['tds'].astype(p2.dtype), 0, 1, 2., 1)
+        assert np.abs(np.asarray(H) - Ho).max() < 1e-6, name
+        assert np.array_equal(Hs, Hso), name
+    dev = [torch.from_numpy(np.ascontiguousarray(d[k].T)).cuda() for k in ('p', 't', 'td')] + \
+          [torch.from_numpy(d[k]).cuda() for k in ('ps', 'ts', 'tds')]
+    H, Hs = stdheight(*dev, 0, 1, 2., 1)
+    assert H.is_cuda and np.abs(H.cpu().numpy() - Ho).max() < 1e-6
+    # pressure grid, start level computed on the device
+    e = make_soundings('C2', cols=(0, 20_000))
+    plp_dev = pres_lev_pos(torch.from_numpy(e['p']).cuda(), torch.from_numpy(e['ps']).cuda())
+    plp = oracle_mod.pres_lev_pos(e['ps'], e['p'][:, None])
+    assert np.array_equal(plp_dev.cpu().numpy(), plp.astype(np.int32))
+    Ho, _ = oracle_mod.stdheight(e['p'][:, None], e['t'].T, e['td'].T, e['ps'], e['ts'], e['tds'], 1, plp, 2., 2, nthreads=8)
+    for pos in (plp, None):
+        H, _ = stdheight(e['p'], e['t'].T, e['td'].T, e['ps'], e['ts'], e['tds'], 1, pos, 2., 2)
+        assert np.abs(np.asarray(H) - Ho).max() < 1e-6
+        assert (np.asarray(H)[0][plp > 1] == -999999).all()
