@@ -299,12 +299,21 @@ __device__ __forceinline__ bool srh_column(const SrhArgs<T>& a, int64_t c, int k
     st.descending = ((float)st.Hs > (float)H);
   }
   int i = 0;
+  // software prefetch: the next level's loads are issued before this level's (long, FP64) step, so the
+  // memory latency hides behind arithmetic instead of stalling the first use
+  T pn = T(0), tn = T(0), tdn = T(0), un = T(0), vn = T(0);
+  auto fetch = [&](int k) {
+    const int64_t off = off3(a, c, ks - 1 + k);
+    un = a.u[off]; vn = a.v[off];
+    if (HG) pn = a.aglh[off];
+    else { pn = (T)ld_p<T, P1D>(a, c, ks - 1 + k); tn = a.t[off]; tdn = a.td[off]; }
+  };
+  if (n3 > 0) fetch(0);
   for (; i < n3; ++i) {
-    const int lev = ks - 1 + i;
-    const int64_t off = off3(a, c, lev);
-    const T uin = a.u[off], vin = a.v[off];
-    if (HG) st.step((double)a.aglh[off], 0.0, 0.0, (double)uin, (double)vin, (float)uin, (float)vin, a.depth);
-    else st.step(ld_p<T, P1D>(a, c, lev), (double)a.t[off], (double)a.td[off], (double)uin, (double)vin, (float)uin, (float)vin, a.depth);
+    const T pc = pn, tc = tn, tdc = tdn, uin = un, vin = vn;
+    if (i + 1 < n3) fetch(i + 1);
+    if (HG) st.step((double)pc, 0.0, 0.0, (double)uin, (double)vin, (float)uin, (float)vin, a.depth);
+    else st.step((double)pc, (double)tc, (double)tdc, (double)uin, (double)vin, (float)uin, (float)vin, a.depth);
     if (st.math_done()) { ++i; break; }            // nothing above can matter if p keeps decreasing
   }
   if (!EXACT)
