@@ -20,6 +20,11 @@
  *                      native (time, level, lat, lon) order of ERA5/HRRR files; zero-copy
  *                      into the kernels when dtype is XCAPE_F32.
  * Level index 0 is the level nearest the surface (reference assumption).
+ * OR-ing XCAPE_LEVELS_TOP_FIRST into `layout` declares the opposite storage order (index 0 = model
+ * top, the order of ERA5 downloads): the library then walks the level axis backwards on the device
+ * (no copy for level-major float32 input).  Level INDICES that cross the boundary — start_3d in,
+ * mulev out — always count from the surface (1 = lowest level), whatever the storage order; 3-D
+ * outputs (xcape_cuda_stdheight's h) are written in the caller's storage order.
  */
 #ifndef XCAPE_B200_H
 #define XCAPE_B200_H
@@ -42,7 +47,8 @@ extern "C" {
 #define XCAPE_ERR_NODEV 3   /* no usable CUDA device */
 
 enum { XCAPE_F32 = 0, XCAPE_F64 = 1 };                 /* dtype of ALL input arrays of a call */
-enum { XCAPE_LEVEL_LAST = 0, XCAPE_LEVEL_MAJOR = 1 };  /* layout of the 3-D input arrays */
+enum { XCAPE_LEVEL_LAST = 0, XCAPE_LEVEL_MAJOR = 1,   /* layout of the 3-D input arrays */
+       XCAPE_LEVELS_TOP_FIRST = 0x100 };               /* flag OR-ed into layout: level axis stored top -> surface */
 enum { XCAPE_MEM_HOST = 0, XCAPE_MEM_DEVICE = 1 };     /* where input AND output pointers live */
 enum { XCAPE_SOURCE_SURFACE = 1, XCAPE_SOURCE_MOST_UNSTABLE = 2, XCAPE_SOURCE_MIXED_LAYER = 3 }; /* core.py:302 */
 enum { XCAPE_ADIABAT_PSEUDO_LIQUID = 1, XCAPE_ADIABAT_REVERSIBLE_LIQUID = 2,

@@ -8,6 +8,8 @@ Bars (BASELINE.json north_star / SURVEY §8d):
   * reference-test tolerance on the goldens: assert_almost_equal decimal=0 (CAPE/CIN/MU),
     decimal=5 (SRH) — test/test_core.py:62-65, 219-220.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -732,3 +734,68 @@ def test_stdheight_layouts_and_memory_spaces(oracle_mod):
         H, _ = stdheight(e['p'], e['t'].T, e['td'].T, e['ps'], e['ts'], e['tds'], 1, pos, 2., 2)
         assert np.abs(np.asarray(H) - Ho).max() < 1e-6
         assert (np.asarray(H)[0][plp > 1] == -999999).all()
+
+
+@pytest.mark.parametrize('cfg,vertical_lev', [('C3', 'sigma'), ('C2', 'pressure')])
+def test_top_first_level_order(core, cfg, vertical_lev):
+    """level_order='top_first' / 'auto' (XCAPE_LEVELS_TOP_FIRST): fields stored model top first, as ERA5
+    downloads are, give bit-identical results to the flipped-by-hand surface-first call — level-last and
+    level-major, float32 and float64, host and device, with the host ring cut into several blocks."""
+    import torch
+    from xcape_b200.stdheight_cuda import stdheight
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings(cfg, cols=(0, 70_000 + 5), winds=True)
+    p1d = (vertical_lev == 'pressure')
+    surf = [d[k] for k in ('ps', 'ts', 'tds')]
+    wsurf = surf + [d['us'], d['vs']]
+    kw = dict(source='most-unstable', pinc=500., vertical_lev=vertical_lev, method='cuda')
+    base = core.calc_cape(d['p'], d['t'], d['td'], *surf, **kw)
+    base_srh = core.calc_srh(d['p'], d['t'], d['td'], d['u'], d['v'], *wsurf, vertical_lev=vertical_lev, output_var='all')
+    flip = lambda a: np.ascontiguousarray(a[..., ::-1])
+    f = {k: flip(d[k]) for k in ('p', 't', 'td', 'u', 'v')}
+    assert f['p'].ravel()[0] < f['p'].ravel()[-1] if p1d else f['p'][0, 0] < f['p'][0, -1]
+    cast = lambda xs, dt: [np.asarray(x, dtype=dt) for x in xs]
+    for order in ('top_first', 'auto'):
+        for dt in (np.float32, np.float64):
+            # level-last host
+            r = core.calc_cape(*cast([f['p'], f['t'], f['td']] + surf, dt), level_order=order, **kw)
+            assert_bitexact(r, base, f'level-last {order} {dt.__name__}')
+            # level-major host (lev_axis=0)
+            lm = [f['p'] if p1d else np.ascontiguousarray(f['p'].T)] + [np.ascontiguousarray(f[k].T) for k in ('t', 'td')]
+            r = core.calc_cape(*cast(lm + surf, dt), level_order=order, lev_axis=0, **kw)
+            assert_bitexact(r, base, f'level-major {order} {dt.__name__}')
+    # device tensors, both layouts
+    tdev = lambda xs: [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in xs]
+    r = core.calc_cape(*tdev([f['p'], f['t'], f['td']] + surf), level_order='top_first', **kw)
+    assert_bitexact([x.cpu().numpy() for x in r], base, 'device level-last')
+    r = core.calc_cape(*tdev([f['p'] if p1d else f['p'].T, f['t'].T, f['td'].T] + surf), level_order='auto', lev_axis=0, **kw)
+    assert_bitexact([x.cpu().numpy() for x in r], base, 'device level-major')
+    # host ring cut into several blocks
+    os.environ['XCAPE_B200_CHUNK_COLS'] = '16384'; os.environ['XCAPE_B200_FIRST_CHUNK_COLS'] = '4096'
+    try:
+        r = core.calc_cape(np.ascontiguousarray(f['p'] if p1d else f['p'].T), np.ascontiguousarray(f['t'].T),
+                           np.ascontiguousarray(f['td'].T), *surf, level_order='top_first', lev_axis=0, **kw)
+        assert_bitexact(r, base, 'level-major host ring')
+    finally:
+        del os.environ['XCAPE_B200_CHUNK_COLS'], os.environ['XCAPE_B200_FIRST_CHUNK_COLS']
+    # SRH, fused chain (float32 and float64, both layouts)
+    for dt in (np.float32, np.float64):
+        b = base_srh if dt is np.float32 else core.calc_srh(*cast([d['p'], d['t'], d['td'], d['u'], d['v']] + wsurf, dt),
+                                                           vertical_lev=vertical_lev, output_var='all')
+        r = core.calc_srh(*cast([f['p'], f['t'], f['td'], f['u'], f['v']] + wsurf, dt), vertical_lev=vertical_lev,
+                          output_var='all', level_order='auto')
+        assert_bitexact(r, b, f'srh level-last {dt.__name__}')
+        lm = [f['p'] if p1d else np.ascontiguousarray(f['p'].T)] + [np.ascontiguousarray(f[k].T) for k in ('t', 'td', 'u', 'v')]
+        r = core.calc_srh(*cast(lm + wsurf, dt), vertical_lev=vertical_lev, output_var='all', level_order='top_first', lev_axis=0)
+        assert_bitexact(r, b, f'srh level-major {dt.__name__}')
+    # heights come back in the caller's (top-first) order
+    tg = 2 if p1d else 1
+    pa = (lambda a: a) if p1d else (lambda a: a.T)
+    H, Hs = stdheight(pa(d['p']), d['t'].T, d['td'].T, *surf, int(p1d), None, 2., tg)
+    Hf, Hsf = stdheight(pa(f['p']), f['t'].T, f['td'].T, *surf, int(p1d), None, 2., tg, top_first=True)
+    assert np.array_equal(np.asarray(Hf)[::-1], np.asarray(H)) and np.array_equal(Hs, Hsf)
+    Hm, _ = stdheight(pa(f['p']) if p1d else np.ascontiguousarray(f['p'].T), np.ascontiguousarray(f['t'].T),
+                      np.ascontiguousarray(f['td'].T), *surf, int(p1d), None, 2., tg, top_first=True)
+    assert np.array_equal(np.asarray(Hm)[::-1], np.asarray(H))
+    with pytest.raises(ValueError):
+        core.calc_cape(d['p'], d['t'], d['td'], *surf, level_order='sideways', **kw)

@@ -104,3 +104,22 @@ def test_synthetic_is_deterministic_and_shardable():
     assert CONFIGS['C2']['grid'] == (721, 1440) and CONFIGS['C5']['nlev'] == 137
     d5 = make_soundings('C5', cols=(0, 8))
     assert d5['p'].shape == (8, 137) and d5['p'][:, -1].max() < 0.2
+
+
+def test_level_order_detection():
+    """core._top_first: 'auto' reads the storage order of the level axis off the pressure array."""
+    from xcape_b200 import core
+    up = np.array([1000., 850., 500., 100.])
+    assert core._top_first(up, -1, 'auto') is False and core._top_first(up[::-1], -1, 'auto') is True
+    p3 = np.broadcast_to(up, (3, 5, 4))
+    assert core._top_first(p3, -1, 'auto') is False and core._top_first(p3[..., ::-1], -1, 'auto') is True
+    pm = np.broadcast_to(up[:, None, None], (4, 3, 5))
+    assert core._top_first(pm, 0, 'auto') is False and core._top_first(pm[::-1], 0, 'auto') is True
+    assert core._top_first(up, -1, 'top_first') is True and core._top_first(up[::-1], -1, 'surface_first') is False
+    with pytest.raises(ValueError):
+        core._top_first(up, -1, 'upside-down')
+    # the dummy backend ignores the order but accepts the keyword
+    t = np.zeros((6, 4), np.float32)
+    r = core.calc_cape(up[::-1].astype(np.float32), t, t, t[:, 0], t[:, 0], t[:, 0], vertical_lev='pressure',
+                       method='dummy', level_order='auto')
+    assert r[0].shape == (6,)

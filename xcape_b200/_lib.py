@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get('XCAPE_B200_LIB') or os.path.join(_HERE, 'libxcape_b20
 # enums of include/xcape_b200.h
 F32, F64 = 0, 1
 LEVEL_LAST, LEVEL_MAJOR = 0, 1
+LEVELS_TOP_FIRST = 0x100      # flag OR-ed into the layout: level axis stored top -> surface
 MEM_HOST, MEM_DEVICE = 0, 1
 FAITHFUL, FAST, FAST_RELAXED = 0, 1, 2
 PRECISION = {'faithful': FAITHFUL, 'fast': FAST, 'fast-relaxed': FAST_RELAXED}

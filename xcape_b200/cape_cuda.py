@@ -17,7 +17,7 @@ from .sharding import column_blocks, run_on_devices
 
 def cape(p_2d, t_2d, td_2d, p_s, t_s, td_s, flag_1d, pres_lev_pos, source, ml_depth, adiabat, pinc,
          type_grid, *, device=0, devices=None, stream=None, precision='faithful', return_status=False,
-         return_counters=False):
+         return_counters=False, top_first=False):
     """
     Parameters follow ``cape_fortran.cape`` (cape_fortran.py:5-46): ``*_2d`` are
     ``(nlev, ngrid)`` (``p_2d`` is ``(nlev, 1)`` / ``(nlev,)`` when ``flag_1d == 1``), ``*_s`` are
@@ -32,7 +32,9 @@ def cape(p_2d, t_2d, td_2d, p_s, t_s, td_s, flag_1d, pres_lev_pos, source, ml_de
     (``'faithful'``: bit-identical to the oracle's SPEC arithmetic; ``'fast'``: FP32-pipe moist
     iteration, tolerance-level parity, MU level still exact), ``return_status``
     (append the per-column status word), ``return_counters`` (append status and the number of
-    moist-adiabat iterations each column ran).
+    moist-adiabat iterations each column ran), ``top_first`` (the level axis is stored model top
+    first, as in ERA5 downloads; it is walked backwards on the device.  ``pres_lev_pos`` in and
+    ``MUlev`` out keep counting from the surface).
 
     Returns ``CAPE, CIN, MUlev, zMUlev`` (float32, float32, int32, float32; shape ``(ngrid,)``)
     — numpy arrays for host inputs, torch CUDA tensors for CUDA-tensor inputs.
@@ -105,7 +107,7 @@ def cape(p_2d, t_2d, td_2d, p_s, t_s, td_s, flag_1d, pres_lev_pos, source, ml_de
 
         rc = L.xcape_cuda_cape(
             A.ptr(p) if p_is_1d else off3(p), off3(t_), off3(td_), off1(ps_, es), off1(ts_, es), off1(tds_, es),
-            C.c_int64(n), nlev, p_is_1d, dt, layout, mem, int(source), int(adiabat),
+            C.c_int64(n), nlev, p_is_1d, dt, layout | (_lib.LEVELS_TOP_FIRST if top_first else 0), mem, int(source), int(adiabat),
             C.c_float(float(ml_depth)), C.c_float(float(pinc)), off1(start, 4),
             off1(cape_o, 4), off1(cin_o, 4), off1(mu_o, 4), off1(z_o, 4), off1(st_o, 4), off1(it_o, 4),
             prec, dev, A.stream_of(ref, stream))

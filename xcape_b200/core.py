@@ -95,6 +95,29 @@ def _unflatten(arrays, grid_shape):
     return [a.reshape(grid_shape) for a in arrays]
 
 
+_LEVEL_ORDERS = ('surface_first', 'top_first', 'auto')
+
+
+def _top_first(p, lev_axis, level_order):
+    """Is the level axis stored model top first?  The reference assumes surface -> top and leaves the
+    flip of e.g. ERA5 downloads (1 -> 1000 hPa) to the caller; here
+    ``level_order='top_first'`` declares it and ``'auto'`` reads it off the pressure array (first
+    column of an N-D ``p``): pressure increasing along the axis means top first."""
+    if level_order not in _LEVEL_ORDERS:
+        raise ValueError(f"`level_order` must be one of: {list(_LEVEL_ORDERS)}")
+    if level_order != 'auto':
+        return level_order == 'top_first'
+    if p.ndim == 1:
+        first, last = p[0], p[-1]
+    elif lev_axis == 0:
+        col = p.reshape(p.shape[0], -1)
+        first, last = col[0, 0], col[-1, 0]
+    else:
+        col = p.reshape(-1, p.shape[-1])
+        first, last = col[0, 0], col[0, -1]
+    return bool(float(first) < float(last))
+
+
 def _any_dask_array(*args):
     return da is not None and any(isinstance(a, da.Array) for a in args)
 
@@ -166,10 +189,11 @@ def _calc_cape_gufunc(*args, **kwargs):
 
 def _calc_cape_numpy(*args, source='surface', ml_depth=500., adiabat='pseudo-liquid', pinc=500.,
                      method='cuda', vertical_lev='sigma', lev_axis=-1, device=0, devices=None,
-                     stream=None, precision='faithful'):
+                     stream=None, precision='faithful', level_order='surface_first'):
     """Flatten to columns, dispatch on ``method``, restore the grid shape (core.py:261-332)."""
     p, t, td, ps, ts, tds = (_as_array(a) for a in args)
     lev_axis = 0 if lev_axis == 0 else -1
+    top_first = _top_first(p, lev_axis, level_order)
     grid_shape = _grid_shape(_shape(t), lev_axis)
 
     p_s1d, t_s1d, td_s1d = _columns_1d([ps, ts, tds])
@@ -192,9 +216,12 @@ def _calc_cape_numpy(*args, source='surface', ml_depth=500., adiabat='pseudo-liq
         from .cape_cuda import cape as _cape_cuda
         # pres_lev_pos=None: computed on the device instead of core.py:286-289's numpy temporaries
         outs = _cape_cuda(p_2d, t_2d, td_2d, p_s1d, t_s1d, td_s1d, flag_1d, None, **opts,
-                          device=device, devices=devices, stream=stream, precision=precision)
+                          device=device, devices=devices, stream=stream, precision=precision,
+                          top_first=top_first)
     elif method in ('fortran', 'dummy'):
         host = [A.to_host_numpy(a) for a in (p_2d, t_2d, td_2d, p_s1d, t_s1d, td_s1d)]
+        if top_first:
+            host[:3] = [np.ascontiguousarray(a[::-1]) for a in host[:3]]
         if method == 'dummy':
             outs = _cape_dummy(*host, **opts)
         else:
@@ -247,10 +274,12 @@ def _calc_srh_gufunc(*args, **kwargs):
 
 
 def _calc_srh_numpy(*args, depth=3000, vertical_lev='sigma', output_var='srh', method='cuda',
-                    lev_axis=-1, device=0, devices=None, stream=None, precision='faithful'):
+                    lev_axis=-1, device=0, devices=None, stream=None, precision='faithful',
+                    level_order='surface_first'):
     """Flatten, dispatch, unflatten (core.py:473-542).  ``aglh0 = 2.`` as in core.py:519."""
     p, t, td, u, v, ps, ts, tds, us, vs = (_as_array(a) for a in args)
     lev_axis = 0 if lev_axis == 0 else -1
+    top_first = _top_first(p, lev_axis, level_order)
     grid_shape = _grid_shape(_shape(t), lev_axis)
     surf = _columns_1d([ps, ts, tds, us, vs])
     if p.ndim == 1 and (t.ndim > 1 or vertical_lev == 'pressure'):
@@ -270,10 +299,13 @@ def _calc_srh_numpy(*args, depth=3000, vertical_lev='sigma', output_var='srh', m
     if method == 'cuda':
         from .srh_cuda import srh_fused
         outs = srh_fused(p_2d, t_2d, td_2d, u_2d, v_2d, *surf, flag_1d, None, depth, 2., type_grid, output,
-                         device=device, devices=devices, stream=stream, precision=precision)
+                         device=device, devices=devices, stream=stream, precision=precision,
+                         top_first=top_first)
     elif method == 'fortran':
         _, srh_f, stdh_f = _reference_shims()
         host = [A.to_host_numpy(a) for a in (p_2d, t_2d, td_2d, u_2d, v_2d, *surf)]
+        if top_first:
+            host[:5] = [np.ascontiguousarray(a[::-1]) for a in host[:5]]
         plp = 1
         if flag_1d:
             plp = np.ma.masked_less(host[5] - host[0], 0).argmin(axis=0) + 1

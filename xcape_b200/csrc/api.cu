@@ -79,30 +79,55 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// `layout` = storage order of the 3-D fields (low byte) | XCAPE_LEVELS_TOP_FIRST
+inline int base_layout(int layout) { return layout & 0xff; }
+inline bool top_first(int layout) { return (layout & XCAPE_LEVELS_TOP_FIRST) != 0; }
+
 int check_common(int64_t ncol, int nlev, int dtype, int layout, int mem) {
   if (ncol < 0) return fail(XCAPE_ERR_ARG, "ncol < 0");
   if (nlev < 1) return fail(XCAPE_ERR_ARG, "nlev < 1");
   if (dtype != XCAPE_F32 && dtype != XCAPE_F64) return fail(XCAPE_ERR_ARG, "dtype must be XCAPE_F32 or XCAPE_F64");
-  if (layout != XCAPE_LEVEL_LAST && layout != XCAPE_LEVEL_MAJOR) return fail(XCAPE_ERR_ARG, "bad layout");
+  if ((layout & ~(0xff | XCAPE_LEVELS_TOP_FIRST)) || (base_layout(layout) != XCAPE_LEVEL_LAST && base_layout(layout) != XCAPE_LEVEL_MAJOR))
+    return fail(XCAPE_ERR_ARG, "bad layout");
   if (mem != XCAPE_MEM_HOST && mem != XCAPE_MEM_DEVICE) return fail(XCAPE_ERR_ARG, "bad mem");
   return XCAPE_OK;
 }
 
-// 3-D field (dtype, layout, leading dimension ld_in for level-major) -> level-major float32.
-// Zero-copy when already float32 level-major.
+// 3-D field (dtype, layout, leading dimension ld_in for level-major) -> level-major float32 with
+// level 0 at the surface.  Zero-copy when already float32 level-major: a top-first level axis is
+// then walked backwards (pointer at the last stored level, negative level stride); the relayout
+// kernels flip it for free by writing through a negative leading dimension.
 int canon3d(const void* in, int dtype, int layout, int64_t ncol, int nlev, int64_t ld_in,
             Scratch& sc, const float** out, int64_t* ld_out, cudaStream_t s) {
-  if (dtype == XCAPE_F32 && layout == XCAPE_LEVEL_MAJOR) { *out = (const float*)in; *ld_out = ld_in; return XCAPE_OK; }
+  const bool rev = top_first(layout);
+  const int lay = base_layout(layout);
+  if (dtype == XCAPE_F32 && lay == XCAPE_LEVEL_MAJOR) {
+    *out = (const float*)in + (rev ? (int64_t)(nlev - 1) * ld_in : 0);
+    *ld_out = rev ? -ld_in : ld_in;
+    return XCAPE_OK;
+  }
   float* buf;
   XC_CUDA(sc.alloc(&buf, (size_t)ncol * nlev));
   *out = buf; *ld_out = ncol;
-  if (layout == XCAPE_LEVEL_LAST) return launch_transpose_cast(in, dtype, buf, ncol, nlev, ncol, s);
-  if (ld_in == ncol) return launch_cast_copy(in, dtype, buf, ncol * nlev, s);
-  for (int k = 0; k < nlev; ++k) {   // strided level-major float64 (host-chunk path never produces this; kept for generality)
-    int rc = launch_cast_copy((const char*)in + (size_t)k * ld_in * esize(dtype), dtype, buf + (size_t)k * ncol, ncol, s);
+  if (lay == XCAPE_LEVEL_LAST)
+    return rev ? launch_transpose_cast(in, dtype, buf + (size_t)(nlev - 1) * ncol, ncol, nlev, -ncol, s)
+               : launch_transpose_cast(in, dtype, buf, ncol, nlev, ncol, s);
+  if (ld_in == ncol && !rev) return launch_cast_copy(in, dtype, buf, ncol * nlev, s);
+  for (int k = 0; k < nlev; ++k) {   // flipped or strided level-major float64
+    const int kin = rev ? nlev - 1 - k : k;
+    int rc = launch_cast_copy((const char*)in + (size_t)kin * ld_in * esize(dtype), dtype, buf + (size_t)k * ncol, ncol, s);
     if (rc) return rc;
   }
   return XCAPE_OK;
+}
+
+// shared 1-D pressure axis in its own dtype, surface first (a flipped copy of nlev elements if needed)
+int canon_p1d(const void* p, int dtype, int layout, int nlev, Scratch& sc, const void** out, cudaStream_t s) {
+  if (!top_first(layout)) { *out = p; return XCAPE_OK; }
+  char* buf;
+  XC_CUDA(sc.alloc(&buf, (size_t)nlev * esize(dtype)));
+  *out = buf;
+  return launch_reverse_copy(p, dtype, buf, nlev, s);
 }
 
 int canon1d(const void* in, int dtype, int64_t n, Scratch& sc, const float** out, cudaStream_t s) {
@@ -131,6 +156,8 @@ int cape_device(const void* p, const void* t, const void* td, const void* ps, co
   int64_t ld2 = ncol;
   if ((rc = canon3d(td, dtype, layout, ncol, nlev, ld_in, sc, &q, &ld2, s))) return rc; a.td = q;
   if (p_is_1d) {
+    const void* pv;
+    if ((rc = canon_p1d(p, dtype, layout, nlev, sc, &pv, s))) return rc; p = pv;
     if ((rc = canon1d(p, dtype, nlev, sc, &q, s))) return rc; a.p = q;
   } else {
     if ((rc = canon3d(p, dtype, layout, ncol, nlev, ld_in, sc, &q, &ldp, s))) return rc; a.p = q;
@@ -167,11 +194,17 @@ int cape_device(const void* p, const void* t, const void* td, const void* ps, co
 // stdheight and SREH are double-precision routines).
 int canon3d_same(const void* in, int dtype, int layout, int64_t ncol, int nlev, int64_t ld_in, Scratch& sc,
                  const void** out, int64_t* ld_out, cudaStream_t s) {
-  if (layout == XCAPE_LEVEL_MAJOR) { *out = in; *ld_out = ld_in; return XCAPE_OK; }
+  const bool rev = top_first(layout);
+  if (base_layout(layout) == XCAPE_LEVEL_MAJOR) {
+    *out = (const char*)in + (rev ? (size_t)(nlev - 1) * ld_in * esize(dtype) : 0);
+    *ld_out = rev ? -ld_in : ld_in;
+    return XCAPE_OK;
+  }
   char* buf;
   XC_CUDA(sc.alloc(&buf, (size_t)ncol * nlev * esize(dtype)));
   *out = buf; *ld_out = ncol;
-  return launch_transpose_same(in, dtype, buf, ncol, nlev, ncol, s);
+  return rev ? launch_transpose_same(in, dtype, buf + (size_t)(nlev - 1) * ncol * esize(dtype), ncol, nlev, -ncol, s)
+             : launch_transpose_same(in, dtype, buf, ncol, nlev, ncol, s);
 }
 
 template <class T>
@@ -190,7 +223,7 @@ int srh_device_t(const void* p, const void* t, const void* td, const void* u, co
     if ((rc = canon3d_same(td, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.td = (const T*)q;
     if ((rc = canon3d_same(u, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.u = (const T*)q;
     if ((rc = canon3d_same(v, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.v = (const T*)q;
-    if (p_is_1d) a.p = (const T*)p;
+    if (p_is_1d) { if ((rc = canon_p1d(p, dtype, layout, nlev, sc, &q, s))) return rc; p = q; a.p = (const T*)q; }
     else { if ((rc = canon3d_same(p, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.p = (const T*)q; }
     a.lev_stride = ld; a.col_stride = 1;
   }
@@ -241,7 +274,7 @@ int height_device_t(const void* p, const void* t, const void* td, const void* ps
   int64_t ld = ncol, l2 = ncol;
   if ((rc = canon3d_same(t, dtype, layout, ncol, nlev, ld_in, sc, &q, &ld, s))) return rc; a.t = (const T*)q;
   if ((rc = canon3d_same(td, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.td = (const T*)q;
-  if (p_is_1d) a.p = (const T*)p;
+  if (p_is_1d) { if ((rc = canon_p1d(p, dtype, layout, nlev, sc, &q, s))) return rc; p = q; a.p = (const T*)q; }
   else { if ((rc = canon3d_same(p, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.p = (const T*)q; }
   a.ps = (const T*)ps; a.ts = (const T*)ts; a.tds = (const T*)tds;
   a.start = start_3d;
@@ -252,8 +285,9 @@ int height_device_t(const void* p, const void* t, const void* td, const void* ps
     a.start = st;
   }
   a.ncol = ncol; a.ld = ld; a.nlev = nlev; a.aglh0 = aglh0; a.h = h; a.hs = hs;
-  if (layout == XCAPE_LEVEL_LAST) { a.h_col_stride = nlev; a.h_lev_stride = 1; }
+  if (base_layout(layout) == XCAPE_LEVEL_LAST) { a.h_col_stride = nlev; a.h_lev_stride = 1; }
   else { a.h_col_stride = 1; a.h_lev_stride = ncol; }
+  if (top_first(layout)) { a.h = h + (int64_t)(nlev - 1) * a.h_lev_stride; a.h_lev_stride = -a.h_lev_stride; }   // heights go back in the caller's order
   return launch_stdheight(a, p_is_1d != 0, s);
 }
 
@@ -606,7 +640,7 @@ int xcape_cuda_cape(const void* p, const void* t, const void* td, const void* ps
   std::vector<HostIn1> in1 = {{ps, es}, {ts, es}, {tds, es}};
   if (start_3d) in1.push_back({start_3d, 4});
   std::vector<HostOut> outs = {{cape, 4, 0}, {cin, 4, 0}, {mulev, 4, 0}, {zmulev, 4, 0}, {status, 4, 0}, {n_iter, 4, 0}};
-  return run_staged(ncol, nlev, layout, es, p_is_1d ? p : nullptr, in3, in1, outs,
+  return run_staged(ncol, nlev, base_layout(layout), es, p_is_1d ? p : nullptr, in3, in1, outs,
                     [&](Block& b, int64_t n, cudaStream_t s) {
                       return cape_device(p_is_1d ? b.p1d : b.in3[2], b.in3[0], b.in3[1], b.in1[0], b.in1[1], b.in1[2], n, nlev,
                                          p_is_1d, dtype, layout, n, source, adiabat, ml_depth, pinc,
@@ -647,7 +681,7 @@ int xcape_cuda_srh(const void* p, const void* t, const void* td, const void* u, 
   std::vector<HostIn1> in1 = {{ps, es}, {ts, es}, {tds, es}, {us, es}, {vs, es}};
   if (start_3d) in1.push_back({start_3d, 4});
   std::vector<HostOut> outs = {{srh_rm, 8, 0}, {srh_lm, 8, 0}, {rm, 8, 0}, {lm, 8, 0}, {mean6, 8, 0}};
-  return run_staged(ncol, nlev, layout, es, p_is_1d ? p : nullptr, in3, in1, outs,
+  return run_staged(ncol, nlev, base_layout(layout), es, p_is_1d ? p : nullptr, in3, in1, outs,
                     [&](Block& b, int64_t n, cudaStream_t s) {
                       return dev(p_is_1d ? b.p1d : b.in3[4], b.in3[0], b.in3[1], b.in3[2], b.in3[3], b.in1[0], b.in1[1],
                                  b.in1[2], b.in1[3], b.in1[4], n, n, start_3d ? (const int32_t*)b.in1[5] : nullptr,
@@ -679,7 +713,7 @@ int xcape_cuda_srh_from_heights(const void* u, const void* v, const void* aglh, 
   std::vector<HostIn1> in1 = {{us, es}, {vs, es}, {aglhs, es}};
   if (start_3d) in1.push_back({start_3d, 4});
   std::vector<HostOut> outs = {{srh_rm, 8, 0}, {srh_lm, 8, 0}, {rm, 8, 0}, {lm, 8, 0}, {mean6, 8, 0}};
-  return run_staged(ncol, nlev, layout, es, nullptr, in3, in1, outs,
+  return run_staged(ncol, nlev, base_layout(layout), es, nullptr, in3, in1, outs,
                     [&](Block& b, int64_t n, cudaStream_t s) {
                       return dev(b.in3[0], b.in3[1], b.in3[2], b.in1[0], b.in1[1], b.in1[2], n,
                                  start_3d ? (const int32_t*)b.in1[3] : nullptr, (double*)b.out[0], (double*)b.out[1],
@@ -710,7 +744,7 @@ int xcape_cuda_stdheight(const void* p, const void* t, const void* td, const voi
   std::vector<HostIn1> in1 = {{ps, es}, {ts, es}, {tds, es}};
   if (start_3d) in1.push_back({start_3d, 4});
   std::vector<HostOut> outs = {{h, 0, 1}, {hs, 8, 0}};
-  return run_staged(ncol, nlev, layout, es, p_is_1d ? p : nullptr, in3, in1, outs,
+  return run_staged(ncol, nlev, base_layout(layout), es, p_is_1d ? p : nullptr, in3, in1, outs,
                     [&](Block& b, int64_t n, cudaStream_t s) {
                       return dev(p_is_1d ? b.p1d : b.in3[2], b.in3[0], b.in3[1], b.in1[0], b.in1[1], b.in1[2], n,
                                  start_3d ? (const int32_t*)b.in1[3] : nullptr, (double*)b.out[0], (double*)b.out[1], s);

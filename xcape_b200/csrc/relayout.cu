@@ -3,6 +3,7 @@
 //     -> level-major [nlev][ld] binary32, fused with the f2py float64->float32 down-cast
 //     (SURVEY §8b "Ownership"); column-block shared-memory staging, both sides coalesced;
 //   * cast_copy: dtype cast of already level-major / 1-D arrays;
+//   * reverse_copy: flips a shared 1-D pressure axis stored top-first (XCAPE_LEVELS_TOP_FIRST);
 //   * pres_lev_pos: core.py:286-289 (numpy masked argmin) evaluated in the input dtype.
 #include "xc_common.cuh"
 #include "relayout.cuh"
@@ -74,6 +75,11 @@ __global__ void __launch_bounds__(256) cast_copy_kernel(const T* __restrict__ in
 }
 
 template <class T>
+__global__ void reverse_copy_kernel(const T* __restrict__ in, T* __restrict__ out, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[n - 1 - i];
+}
+
+template <class T>
 __global__ void __launch_bounds__(256) pres_lev_pos_kernel(const T* __restrict__ p, const T* __restrict__ ps,
                                                            int64_t ncol, int nlev, int32_t* __restrict__ start) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -134,6 +140,14 @@ int launch_cast_copy(const void* in, int dtype, float* out, int64_t n, cudaStrea
   if (n <= 0) return XCAPE_OK;
   if (dtype == XCAPE_F64) cast_copy_kernel<double><<<grid_for(n, 256), 256, 0, s>>>((const double*)in, out, n);
   else cast_copy_kernel<float><<<grid_for(n, 256), 256, 0, s>>>((const float*)in, out, n);
+  XC_LAUNCH_CHECK();
+  return XCAPE_OK;
+}
+
+int launch_reverse_copy(const void* in, int dtype, void* out, int n, cudaStream_t s) {
+  if (n <= 0) return XCAPE_OK;
+  if (dtype == XCAPE_F64) reverse_copy_kernel<double><<<1, 256, 0, s>>>((const double*)in, (double*)out, n);
+  else reverse_copy_kernel<float><<<1, 256, 0, s>>>((const float*)in, (float*)out, n);
   XC_LAUNCH_CHECK();
   return XCAPE_OK;
 }

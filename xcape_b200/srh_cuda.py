@@ -17,7 +17,8 @@ from .sharding import column_blocks, run_on_devices
 
 
 def srh_fused(p_2d, t_2d, td_2d, u_2d, v_2d, p_s, t_s, td_s, u_s, v_s, flag_1d, pres_lev_pos, depth,
-              aglh0, type_grid, output, *, device=0, devices=None, stream=None, precision='faithful'):
+              aglh0, type_grid, output, *, device=0, devices=None, stream=None, precision='faithful',
+              top_first=False):
     """
     Arguments are the union of ``stdheight.stdheight`` (stdheight.py:5) and ``srh.srh``
     (srh.py:4): ``*_2d`` are ``(nlev, ngrid)``, ``*_s`` are ``(ngrid,)``; ``pres_lev_pos`` may be
@@ -26,6 +27,7 @@ def srh_fused(p_2d, t_2d, td_2d, u_2d, v_2d, p_s, t_s, td_s, u_s, v_s, flag_1d, 
     ``(srh_rm, srh_lm, rm(2, ngrid), lm(2, ngrid), mean_6km(2, ngrid))`` like srh.py:63-66.
     srh_* are float64, the storm-motion arrays float32.  ``precision='fast'``
     evaluates the hypsometric height chain in binary32 (within ~1e-3 m2/s2 of the reference).
+    ``top_first``: the level axis is stored model top first and walked backwards on the device.
     """
     L = _lib.lib()
     if precision not in ('faithful', 'fast'):
@@ -94,7 +96,8 @@ def srh_fused(p_2d, t_2d, td_2d, u_2d, v_2d, p_s, t_s, td_s, u_s, v_s, flag_1d, 
         rc = L.xcape_cuda_srh(
             A.ptr(p) if p_is_1d else off3(p), off3(t_), off3(td_), off3(u_), off3(v_),
             off1(ps_, es), off1(ts_, es), off1(tds_, es), off1(us_, es), off1(vs_, es),
-            C.c_int64(n), nlev, p_is_1d, dt, layout, mem, C.c_double(float(depth)), C.c_double(float(aglh0)),
+            C.c_int64(n), nlev, p_is_1d, dt, layout | (_lib.LEVELS_TOP_FIRST if top_first else 0), mem,
+            C.c_double(float(depth)), C.c_double(float(aglh0)),
             off1(start, 4), off1(srm, 8), off1(slm, 8), off1(rm, 8), off1(lm, 8), off1(m6, 8),
             prec, dev, A.stream_of(ref, stream))
         _lib.check(rc)
@@ -111,10 +114,12 @@ def srh_fused(p_2d, t_2d, td_2d, u_2d, v_2d, p_s, t_s, td_s, u_s, v_s, flag_1d, 
     return srm, slm, tr(rm), tr(lm), tr(m6)
 
 
-def srh(u_2d, v_2d, aglh_2d, u_s, v_s, aglh_s, pres_lev_pos, depth, type_grid, output, *, device=0, stream=None):
+def srh(u_2d, v_2d, aglh_2d, u_s, v_s, aglh_s, pres_lev_pos, depth, type_grid, output, *, device=0, stream=None,
+        top_first=False):
     """Same arguments and returns as ``xcape.srh.srh`` (srh.py:4-66): winds and heights ``(nlev,
     ngrid)``, surface values ``(ngrid,)``; ``pres_lev_pos`` (1-based first level used) only matters
-    for ``type_grid == 2``.  Replaces ``bunkers_loop_*`` + ``loop_sreh_*``."""
+    for ``type_grid == 2``.  Replaces ``bunkers_loop_*`` + ``loop_sreh_*``.  ``top_first``: level axis
+    stored model top first (``pres_lev_pos`` still counts from the surface)."""
     L = _lib.lib()
     nlev, ngrid = u_2d.shape
     if type_grid not in (1, 2):
@@ -138,7 +143,8 @@ def srh(u_2d, v_2d, aglh_2d, u_s, v_s, aglh_s, pres_lev_pos, depth, type_grid, o
     lm = A.empty_like_host_or_device(ref, (ngrid, 2), 'float32') if want_all else None
     m6 = A.empty_like_host_or_device(ref, (ngrid, 2), 'float32') if want_all else None
     rc = L.xcape_cuda_srh_from_heights(A.ptr(u_), A.ptr(v_), A.ptr(h_), A.ptr(us_), A.ptr(vs_), A.ptr(hs_),
-                                       C.c_int64(ngrid), nlev, dt, layout, mem, C.c_double(float(depth)), A.ptr(start),
+                                       C.c_int64(ngrid), nlev, dt, layout | (_lib.LEVELS_TOP_FIRST if top_first else 0), mem,
+                                       C.c_double(float(depth)), A.ptr(start),
                                        A.ptr(srm), A.ptr(slm), A.ptr(rm), A.ptr(lm), A.ptr(m6),
                                        A.device_of(ref, device), A.stream_of(ref, stream))
     _lib.check(rc)

@@ -9,10 +9,12 @@ from . import _lib
 
 
 def stdheight(p_2d, t_2d, td_2d, p_s, t_s, td_s, flag_1d, pres_lev_pos, aglh0, type_grid, *,
-              device=0, stream=None):
+              device=0, stream=None, top_first=False):
     """Same arguments as ``xcape.stdheight.stdheight``; returns ``(H2D (nlev, ngrid) float64,
     H_s (ngrid,) float64)``.  Levels below ``pres_lev_pos`` are -999999
-    (stdheight_2D_pressure_lev.f90:85-87).  ``aglh0`` must be a scalar here."""
+    (stdheight_2D_pressure_lev.f90:85-87).  ``aglh0`` must be a scalar here.  ``top_first``:
+    the level axis of the inputs is stored model top first; ``H2D`` comes back in that same order
+    (``pres_lev_pos`` counts from the surface)."""
     L = _lib.lib()
     nlev, ngrid = t_2d.shape
     if not np.isscalar(aglh0):
@@ -43,7 +45,8 @@ def stdheight(p_2d, t_2d, td_2d, p_s, t_s, td_s, flag_1d, pres_lev_pos, aglh0, t
         h_view = h.t() if A.is_cuda(ref) else h.T
     hs = A.empty_like_host_or_device(ref, (ngrid,), 'float64')
     rc = L.xcape_cuda_stdheight(A.ptr(p), A.ptr(t_), A.ptr(td_), A.ptr(ps_), A.ptr(ts_), A.ptr(tds_),
-                                C.c_int64(ngrid), nlev, p_is_1d, dt, layout, mem, C.c_double(float(aglh0)),
+                                C.c_int64(ngrid), nlev, p_is_1d, dt, layout | (_lib.LEVELS_TOP_FIRST if top_first else 0), mem,
+                                C.c_double(float(aglh0)),
                                 A.ptr(start), A.ptr(h), A.ptr(hs), A.device_of(ref, device),
                                 A.stream_of(ref, stream))
     _lib.check(rc)
