@@ -154,7 +154,8 @@ XCAPE_API const char* xcape_cuda_version(void);         /* "xcape_b200 <semver> 
 XCAPE_API int64_t xcape_cuda_kernel_launches(void);     /* kernels launched by this library so far (process-wide) */
 /* The library keeps its stream-ordered scratch (relayout buffers, staging blocks) in a private
  * cudaMemPool per device and never returns it to the driver on its own (re-mapping ~300 MB per call cost
- * 5 ms per ERA5 field).  This call synchronises `device` and hands the cached memory back. */
+ * 5 ms per ERA5 field).  This call synchronises `device` and hands the cached memory back, along
+ * with the idle pinned host staging buffers of the host-pointer path. */
 XCAPE_API int xcape_cuda_release_memory(int device);
 /* Measured arithmetic peaks of `device` (roofline denominators the driver's MEASURED_PEAKS.json
  * lacks): dependent-chain-free FFMA / DFMA loops, 2 flop per FMA, best of `reps` launches. */

@@ -799,3 +799,30 @@ def test_top_first_level_order(core, cfg, vertical_lev):
     assert np.array_equal(np.asarray(Hm)[::-1], np.asarray(H))
     with pytest.raises(ValueError):
         core.calc_cape(d['p'], d['t'], d['td'], *surf, level_order='sideways', **kw)
+
+
+def test_streamed_time_steps_match_direct_calls(core, tmp_path):
+    """xcape_b200.stream: memory-mapped level-major time steps dealt to two worker threads (both on GPU 0
+    when the box has one) give, in order, exactly what one direct call per step gives."""
+    import torch
+    from xcape_b200.stream import stream_cape, stream_srh
+    from xcape_b200.synthetic import make_soundings
+    devs = [0, 1] if torch.cuda.device_count() > 1 else [0, 0]
+    steps, direct, wsteps, wdirect = [], [], [], []
+    for k in range(5):
+        d = make_soundings('C2', cols=(k * 30_000, k * 30_000 + 30_000 + k), winds=True)
+        for name in ('t', 'td', 'u', 'v'):
+            np.save(tmp_path / f'{name}{k}.npy', np.ascontiguousarray(d[name].T))        # (level, column) on disk
+        mm = {name: np.load(tmp_path / f'{name}{k}.npy', mmap_mode='r') for name in ('t', 'td', 'u', 'v')}
+        surf = (d['ps'], d['ts'], d['tds'])
+        steps.append((d['p'], mm['t'], mm['td'], *surf))
+        wsteps.append((d['p'], mm['t'], mm['td'], mm['u'], mm['v'], *surf, d['us'], d['vs']))
+        direct.append(core.calc_cape(d['p'], d['t'], d['td'], *surf, source='most-unstable', vertical_lev='pressure'))
+        wdirect.append(core.calc_srh(d['p'], d['t'], d['td'], d['u'], d['v'], *surf, d['us'], d['vs'], vertical_lev='pressure'))
+    got = list(stream_cape(steps, devices=devs, prefetch=2, readers=2, source='most-unstable', vertical_lev='pressure',
+                           lev_axis=0))
+    assert len(got) == 5
+    for k in range(5):
+        assert_bitexact(got[k], direct[k], f'step {k}')
+    for k, r in enumerate(stream_srh(wsteps, devices=devs, vertical_lev='pressure', lev_axis=0)):
+        assert_bitexact(r, wdirect[k], f'srh step {k}')

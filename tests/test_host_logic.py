@@ -123,3 +123,46 @@ def test_level_order_detection():
     r = core.calc_cape(up[::-1].astype(np.float32), t, t, t[:, 0], t[:, 0], t[:, 0], vertical_lev='pressure',
                        method='dummy', level_order='auto')
     assert r[0].shape == (6,)
+
+
+def test_stream_pipeline_order_errors_and_early_stop(tmp_path):
+    """xcape_b200.stream: steps come back in order whatever the worker/reader counts, memory-mapped
+    steps are read on the reader threads, loader exceptions reach the consumer, an abandoned
+    generator winds its threads down."""
+    import threading
+    from xcape_b200.stream import _materialise, stream_cape, stream_srh
+    steps = []
+    for k in range(9):
+        np.save(tmp_path / f't{k}.npy', np.full((6, 5, 4), k, np.float32))
+        m = np.load(tmp_path / f't{k}.npy', mmap_mode='r')
+        steps.append((m, m, m, m[..., 0], m[..., 0], m[..., 0]))
+    got, borrowed = _materialise(steps[3])
+    assert borrowed == []
+    assert all(type(a) is np.ndarray and a.flags['C_CONTIGUOUS'] for a in got) and got[3].shape == (6, 5)
+    before = threading.active_count()
+    for devices, readers, prefetch in (([0], 1, 1), ([0, 1, 2], 2, 2), ([0, 1], 4, 3)):
+        out = list(stream_cape(steps, devices=devices, readers=readers, prefetch=prefetch, method='dummy',
+                               source='most-unstable'))
+        assert len(out) == 9 and all(len(o) == 4 and o[0].shape == (6, 5) for o in out)
+    from xcape_b200.stream import _stream
+    import time
+
+    def tag(*arrays, device, **kw):                # later steps finish first
+        time.sleep(0.002 * (9 - int(arrays[0].ravel()[0])))
+        return int(arrays[0].ravel()[0]), device
+    out = list(_stream(tag, steps, [0, 1, 2], 3, 2, {}))
+    assert [k for k, _ in out] == list(range(9)) and {d for _, d in out} <= {0, 1, 2}
+    assert list(stream_cape([], method='dummy')) == []
+    g = stream_cape([lambda s=s: s for s in steps], method='dummy')
+    assert next(g)[0].shape == (6, 5)
+    g.close()
+
+    def bad():
+        raise OSError('disk gone')
+    with pytest.raises(OSError):
+        list(stream_cape([steps[0], bad, steps[1]], method='dummy'))
+    with pytest.raises(ValueError):
+        stream_cape(steps, devices=[], method='dummy')
+    with pytest.raises(ValueError):
+        list(stream_srh([steps[0]], method='cuda'))          # arity error surfaces from calc_srh
+    assert threading.active_count() == before

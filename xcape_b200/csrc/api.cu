@@ -355,30 +355,52 @@ struct PinnedCache {
     for (auto& e : ents)
       if (e.p == p) e.used = false;
   }
+  void trim() {                                   // give idle buffers back (xcape_cuda_release_memory)
+    std::lock_guard<std::mutex> lk(mu);
+    std::vector<Ent> kept;
+    for (auto& e : ents) {
+      if (e.used) kept.push_back(e);
+      else cudaFreeHost(e.p);
+    }
+    ents.swap(kept);
+  }
 };
 PinnedCache g_pinned;
 
-// Multi-threaded host copy into a pinned staging buffer (pageable caller memory would otherwise go
+// Multi-threaded host copies into a pinned staging buffer (pageable caller memory would otherwise go
 // through the driver's single bounce buffer at ~12 GB/s and block the enqueuing thread).
-void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+inline int copy_threads() {
   static const int nthr = (int)env_i64("XCAPE_B200_COPY_THREADS", std::min<int64_t>(8, std::max<int64_t>(1, std::thread::hardware_concurrency() / 2)), 1, 64);
-  if (bytes < ((size_t)4 << 20) || nthr == 1) { memcpy(dst, src, bytes); return; }
+  return nthr;
+}
+// fn(part) for part in [0, nparts) on up to copy_threads() host threads (the caller's included)
+template <class F>
+void parallel_parts(int nparts, F fn) {
+  const int nthr = std::min(copy_threads(), nparts);
+  if (nthr <= 1) { for (int q = 0; q < nparts; ++q) fn(q); return; }
+  std::atomic<int> next{0};
+  auto work = [&] { for (int q; (q = next.fetch_add(1)) < nparts;) fn(q); };
   std::vector<std::thread> th;
-  const size_t part = ((bytes / nthr) + 4095) & ~(size_t)4095;
-  for (int t = 0; t < nthr; ++t) {
-    const size_t a = (size_t)t * part;
-    if (a >= bytes) break;
-    const size_t n = std::min(part, bytes - a);
-    th.emplace_back([=] { memcpy((char*)dst + a, (const char*)src + a, n); });
-  }
+  for (int t = 1; t < nthr; ++t) th.emplace_back(work);
+  work();
   for (auto& x : th) x.join();
+}
+void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+  if (bytes < ((size_t)4 << 20) || copy_threads() == 1) { memcpy(dst, src, bytes); return; }
+  const size_t part = (size_t)1 << 20;
+  const int nparts = (int)((bytes + part - 1) / part);
+  parallel_parts(nparts, [=](int q) {
+    const size_t a = (size_t)q * part;
+    memcpy((char*)dst + a, (const char*)src + a, std::min(part, bytes - a));
+  });
 }
 
 // columns [c0, c0+n) of a 3-D host field -> dense block of the same layout in `dst` (host)
 void stage_field(void* dst, const void* src, int layout, int64_t ncol, int nlev, int64_t c0, int64_t n, size_t es) {
   if (layout == XCAPE_LEVEL_LAST) { parallel_memcpy(dst, (const char*)src + (size_t)c0 * nlev * es, (size_t)n * nlev * es); return; }
-  for (int k = 0; k < nlev; ++k)
-    memcpy((char*)dst + (size_t)k * n * es, (const char*)src + ((size_t)k * ncol + c0) * es, (size_t)n * es);
+  auto row = [=](int k) { memcpy((char*)dst + (size_t)k * n * es, (const char*)src + ((size_t)k * ncol + c0) * es, (size_t)n * es); };
+  if ((size_t)n * nlev * es < ((size_t)4 << 20)) { for (int k = 0; k < nlev; ++k) row(k); return; }
+  parallel_parts(nlev, row);                       // level-major: one row of the block per level
 }
 
 bool is_pageable_host(const void* p) {
@@ -590,6 +612,7 @@ int xcape_cuda_release_memory(int device) {
   if (!dg.ok) return fail(XCAPE_ERR_NODEV, "cudaSetDevice failed");
   XC_CUDA(cudaDeviceSynchronize());
   if (cudaMemPool_t pool = pool_for_current_device()) XC_CUDA(cudaMemPoolTrimTo(pool, 0));
+  g_pinned.trim();
   return XCAPE_OK;
 }
 
