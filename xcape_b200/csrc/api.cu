@@ -309,7 +309,7 @@ inline int64_t env_i64(const char* name, int64_t dflt, int64_t lo, int64_t hi) {
 // grow geometrically from XCAPE_B200_FIRST_CHUNK_COLS to XCAPE_B200_CHUNK_COLS: a small first block
 // gets the GPU busy after ~0.3 ms of H2D, large later blocks keep per-kernel tails rare.
 inline int64_t chunk_cols() { return env_i64("XCAPE_B200_CHUNK_COLS", 1 << 18, 1024, 1 << 26); }
-inline int64_t first_chunk_cols() { return env_i64("XCAPE_B200_FIRST_CHUNK_COLS", 1 << 15, 1024, 1 << 26); }
+inline int64_t first_chunk_cols() { return env_i64("XCAPE_B200_FIRST_CHUNK_COLS", 1 << 16, 1024, 1 << 26); }
 inline int ring_streams() { return (int)env_i64("XCAPE_B200_STREAMS", 4, 1, kMaxStreams); }
 
 struct HostIn3 { const void* host; };                    // [ncol][nlev] or [nlev][ncol], es bytes/element
@@ -493,6 +493,14 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
     return XCAPE_OK;
   };
 
+  // XCAPE_B200_TRACE: device-side timeline of every block (timing events; diagnostics only)
+  struct BlockEv { cudaEvent_t e[4] = {}; int64_t n = 0; int slot = 0; };
+  std::vector<BlockEv> tl;
+  cudaEvent_t tl_base = nullptr;
+  auto mark = [&](cudaEvent_t* e, cudaStream_t s) {
+    if (cudaEventCreate(e) == cudaSuccess) cudaEventRecord(*e, s);
+  };
+
   auto body = [&]() -> int {
     int cur_dev = 0;
     XC_CUDA(cudaGetDevice(&cur_dev));
@@ -536,6 +544,11 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
       cudaStream_t s = st[i];
       int r = drain(i);                            // slot reuse: its previous block must have left
       if (r) return r;
+      if (trace) {
+        if (!tl_base) mark(&tl_base, s);
+        tl.emplace_back(); tl.back().n = n; tl.back().slot = i;
+        mark(&tl.back().e[0], s);
+      }
       for (size_t k = 0; k < in3.size(); ++k) {
         if (stage3[i][k]) {        // pageable: host threads fill the slot's pinned buffer, then a true async H2D
           stage_field(stage3[i][k], in3[k].host, layout, ncol, nlev, c0, n, es);
@@ -549,13 +562,16 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
         if (stage1[i][k]) { memcpy(stage1[i][k], src, (size_t)n * in1[k].es); src = stage1[i][k]; }
         XC_CUDA(cudaMemcpyAsync(b[i].in1[k], src, (size_t)n * in1[k].es, cudaMemcpyHostToDevice, s));
       }
+      if (trace) mark(&tl.back().e[1], s);
       if ((r = launch(b[i], n, s))) return r;
+      if (trace) mark(&tl.back().e[2], s);
       for (size_t k = 0; k < outs.size(); ++k) {
         if (!outs[k].host) continue;
         if (outs[k].is3d) XC_CUDA(d2h_field(outs[k].host, b[i].out[k], layout, ncol, nlev, c0, n, 8, s));
         else if (staged[k]) XC_CUDA(cudaMemcpyAsync(stage[i][k], b[i].out[k], (size_t)n * outs[k].bytes_per_col, cudaMemcpyDeviceToHost, s));
         else XC_CUDA(cudaMemcpyAsync((char*)outs[k].host + (size_t)c0 * outs[k].bytes_per_col, b[i].out[k], (size_t)n * outs[k].bytes_per_col, cudaMemcpyDeviceToHost, s));
       }
+      if (trace) mark(&tl.back().e[3], s);
       XC_CUDA(cudaEventRecord(done[i], s));
       pend[i].on = true; pend[i].c0 = c0; pend[i].n = n;
       c0 += n;
@@ -585,6 +601,16 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
     for (void* h : stage1[i]) if (h) g_pinned.release(h);
   }
   if (ring) g_rings.release(ring);
+  if (trace && tl_base) {
+    for (size_t q = 0; q < tl.size(); ++q) {
+      float t[4] = {-1, -1, -1, -1};
+      for (int j = 0; j < 4; ++j)
+        if (tl[q].e[j]) { if (!rc) cudaEventElapsedTime(&t[j], tl_base, tl[q].e[j]); cudaEventDestroy(tl[q].e[j]); }
+      fprintf(stderr, "[xcape_b200]   block %2zu slot %d n=%7lld: h2d %.3f..%.3f ms, kernels ..%.3f ms, d2h ..%.3f ms (device clock)\n",
+              q, tl[q].slot, (long long)tl[q].n, t[0], t[1], t[2], t[3]);
+    }
+    cudaEventDestroy(tl_base);
+  }
   if (rc) { cudaGetLastError(); g_last_error = keep; }
   if (trace) fprintf(stderr, "[xcape_b200] run_staged ncol=%lld blocks=%d streams=%d: body %.3f ms, teardown %.3f ms\n",
                      (long long)ncol, nblocks, nstream, t_body - t_begin, now() - t_body);
