@@ -157,6 +157,14 @@ XCAPE_API int64_t xcape_cuda_kernel_launches(void);     /* kernels launched by t
  * 5 ms per ERA5 field).  This call synchronises `device` and hands the cached memory back, along
  * with the idle pinned host staging buffers of the host-pointer path. */
 XCAPE_API int xcape_cuda_release_memory(int device);
+/* Dew point (degC) from pressure (hPa) and specific humidity q (kg/kg), elementwise over a 3-D field —
+ * the conversion ERA5 users run ahead of calc_cape (the reference ships none: doc/tutorial.rst:19-23;
+ * SURVEY 8f-3).  The inverse of the kernels' own saturation law (getqvs, CAPE_CODE_model_lev.f90:570-581):
+ * r = q/(1-q), e = p r/(eps + r), L = ln(e/6.112), Td = 243.5 L/(17.67 - L).  q and td: `dtype`, same
+ * layout; p: [nlev] when p_is_1d, else like q.  q below q_min is raised to q_min first (0 keeps q as is;
+ * q <= 0 then yields NaN / -inf like the formula). */
+XCAPE_API int xcape_cuda_dewpoint_from_q(const void* p, const void* q, int64_t ncol, int nlev, int p_is_1d, int dtype,
+                                         int layout, int mem, double q_min, void* td, int device, void* stream);
 /* Measured arithmetic peaks of `device` (roofline denominators the driver's MEASURED_PEAKS.json
  * lacks): dependent-chain-free FFMA / DFMA loops, 2 flop per FMA, best of `reps` launches. */
 XCAPE_API int xcape_cuda_measure_peaks(int device, int reps, double* fp32_tflops, double* fp64_tflops);

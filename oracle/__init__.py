@@ -274,3 +274,22 @@ def calc_srh_ref(p, t, td, u, v, ps, ts, tds, us, vs, depth=3000, vertical_lev='
     # reference quirk kept: a plain C-order reshape of the (2, ncol) array (core.py:65-79)
     rm, lm, m6 = (np.reshape(a, tgt2) for a in out[2:])
     return res + [rm[0], rm[1], lm[0], lm[1], m6[0], m6[1]]
+
+
+def dewpoint_from_q_ref(p_hpa, q, q_min=1e-10):
+    """float64 numpy statement of xcape_cuda_dewpoint_from_q (parity unpinned: the reference has no
+    such routine).  Inverse of getqvs (CAPE_CODE_model_lev.f90:570-581): r = q/(1-q), e = p r/(eps+r),
+    L = ln(e/6.112), Td = 243.5 L/(17.67 - L) degC."""
+    p_hpa = np.asarray(p_hpa, np.float64)
+    q = np.maximum(np.asarray(q, np.float64), q_min) if q_min > 0 else np.asarray(q, np.float64)
+    r = q / (1.0 - q)
+    e = p_hpa * r / (287.04 / 461.5 + r)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        L = np.log(e / 6.112)
+        return 243.5 * L / (17.67 - L)
+
+
+def qvs_ref(p_pa, t_k):
+    """getqvs (CAPE_CODE_model_lev.f90:570-581) in float64: saturation mixing ratio over liquid."""
+    es = 611.2 * np.exp(17.67 * (t_k - 273.15) / (t_k - 29.65))
+    return (287.04 / 461.5) * es / (p_pa - es)

@@ -826,3 +826,53 @@ def test_streamed_time_steps_match_direct_calls(core, tmp_path):
         assert_bitexact(got[k], direct[k], f'step {k}')
     for k, r in enumerate(stream_srh(wsteps, devices=devs, vertical_lev='pressure', lev_axis=0)):
         assert_bitexact(r, wdirect[k], f'srh step {k}')
+
+
+def test_dewpoint_from_q(oracle_mod):
+    """xcape_cuda_dewpoint_from_q against its float64 formula (parity unpinned by the reference), every
+    layout / dtype / memory space, the host ring across blocks, and the round trip through the CAPE
+    kernels' own saturation law: qvs(p, Td(q)) gives back the mixing ratio q/(1-q)."""
+    import torch
+    from xcape_b200.synthetic import make_soundings
+    from xcape_b200.thermo import dewpoint_from_q
+    d = make_soundings('C3', cols=(0, 50_000 + 11))
+    p, td = d['p'].astype(np.float64), d['td'].astype(np.float64)
+    r = oracle_mod.qvs_ref(100.0 * p, td + 273.15)
+    q64 = r / (1.0 + r)
+    assert np.abs(oracle_mod.dewpoint_from_q_ref(p, q64, q_min=0.0) - td).max() < 1e-9    # the formula really is the inverse
+    assert np.abs(dewpoint_from_q(p, q64, q_min=0.0) - td).max() < 1e-9
+    ref = oracle_mod.dewpoint_from_q_ref(p, q64)               # default floor (the synthetic stratosphere is far below it)
+    got = dewpoint_from_q(p, q64)
+    assert got.dtype == np.float64 and got.shape == q64.shape and np.abs(got - ref).max() < 1e-10
+    q32, p32 = q64.astype(np.float32), d['p']
+    ref32 = oracle_mod.dewpoint_from_q_ref(p32, q32)
+    tol = lambda x: 2.0 * np.spacing(np.abs(x).astype(np.float32)).astype(np.float64) + 1e-30
+    got32 = dewpoint_from_q(p32, q32)
+    assert got32.dtype == np.float32 and (np.abs(got32 - ref32) <= tol(ref32)).all()
+    # level-major, device tensors, several host blocks
+    lm = dewpoint_from_q(np.ascontiguousarray(p32.T), np.ascontiguousarray(q32.T), lev_axis=0)
+    assert np.array_equal(lm.T, got32)
+    dev = dewpoint_from_q(torch.from_numpy(p32).cuda(), torch.from_numpy(q32).cuda())
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), got32)
+    os.environ['XCAPE_B200_CHUNK_COLS'] = '16384'; os.environ['XCAPE_B200_FIRST_CHUNK_COLS'] = '4096'
+    try:
+        assert np.array_equal(dewpoint_from_q(p32, q32), got32)
+        assert np.array_equal(dewpoint_from_q(np.ascontiguousarray(p32.T), np.ascontiguousarray(q32.T), lev_axis=0).T, got32)
+    finally:
+        del os.environ['XCAPE_B200_CHUNK_COLS'], os.environ['XCAPE_B200_FIRST_CHUNK_COLS']
+    # 1-D pressure axis (pressure-level grids), N-D grid shape, q floor and q <= 0
+    e = make_soundings('C2', cols=(0, 6000))
+    r2 = oracle_mod.qvs_ref(100.0 * e['p'].astype(np.float64)[None, :],
+                            np.maximum(e['td'].astype(np.float64), -110.0) + 273.15)   # the synthetic 1 hPa dew points are unphysical
+    q2 = (r2 / (1.0 + r2)).astype(np.float32).reshape(60, 100, -1)
+    g = dewpoint_from_q(e['p'], q2)
+    ref2 = oracle_mod.dewpoint_from_q_ref(e['p'][None, None, :], q2)
+    assert g.shape == q2.shape and (np.abs(g - ref2) <= tol(ref2)).all()
+    g0 = dewpoint_from_q(np.ascontiguousarray(e['p']), np.ascontiguousarray(np.moveaxis(q2, -1, 0)), lev_axis=0)
+    assert np.array_equal(np.moveaxis(g0, 0, -1), g)
+    z = np.zeros((4, 37), np.float32)
+    floor = dewpoint_from_q(e['p'], z)
+    assert np.isfinite(floor).all() and (floor < -90).all()
+    assert not np.isfinite(dewpoint_from_q(e['p'], z, q_min=0.0)).any()
+    with pytest.raises(ValueError):
+        dewpoint_from_q(e['p'][:5], q2)

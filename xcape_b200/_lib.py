@@ -21,7 +21,8 @@ OK, ERR_ARG, ERR_CUDA, ERR_NODEV = 0, 1, 2, 3
 # every symbol include/xcape_b200.h declares (tests check the library exports all of them)
 SYMBOLS = ('xcape_cuda_cape', 'xcape_cuda_srh', 'xcape_cuda_srh_from_heights', 'xcape_cuda_stdheight', 'xcape_cuda_pres_lev_pos',
            'xcape_cuda_last_error', 'xcape_cuda_device_count', 'xcape_cuda_version',
-           'xcape_cuda_kernel_launches', 'xcape_cuda_measure_peaks', 'xcape_cuda_release_memory')
+           'xcape_cuda_kernel_launches', 'xcape_cuda_measure_peaks', 'xcape_cuda_release_memory',
+           'xcape_cuda_dewpoint_from_q')
 
 _lib = None
 
@@ -58,6 +59,8 @@ def lib():
         L.xcape_cuda_stdheight.argtypes = [vp] * 6 + [i64, i32, i32, i32, i32, i32, f64, vp, vp, vp, i32, vp]
         L.xcape_cuda_pres_lev_pos.restype = i32
         L.xcape_cuda_pres_lev_pos.argtypes = [vp, vp, i64, i32, i32, i32, vp, i32, vp]
+        L.xcape_cuda_dewpoint_from_q.restype = i32
+        L.xcape_cuda_dewpoint_from_q.argtypes = [vp, vp, i64, i32, i32, i32, i32, i32, f64, vp, i32, vp]
         L.xcape_cuda_last_error.restype = C.c_char_p
         L.xcape_cuda_version.restype = C.c_char_p
         L.xcape_cuda_device_count.restype = i32

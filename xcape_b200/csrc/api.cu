@@ -14,6 +14,7 @@
 #include "cape_kernel.cuh"
 #include "srh_launch.cuh"
 #include "peaks.cuh"
+#include "thermo.cuh"
 
 namespace xc {
 
@@ -314,7 +315,7 @@ inline int ring_streams() { return (int)env_i64("XCAPE_B200_STREAMS", 4, 1, kMax
 
 struct HostIn3 { const void* host; };                    // [ncol][nlev] or [nlev][ncol], es bytes/element
 struct HostIn1 { const void* host; size_t es; };          // [ncol]
-struct HostOut { void* host; size_t bytes_per_col; int is3d; };   // per-column outputs (is3d: nlev*8 bytes per column, layout-aware)
+struct HostOut { void* host; size_t bytes_per_col; int is3d; };   // per-column outputs; is3d: a 3-D field in the inputs' layout, bytes_per_col = bytes per ELEMENT
 
 struct Block {
   std::vector<void*> in3, in1, out;
@@ -522,7 +523,7 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
         stage1[i].push_back(h);
       }
       for (size_t k = 0; k < outs.size(); ++k) {
-        void* q; XC_CUDA(pool_alloc(&q, (size_t)chunk * (outs[k].is3d ? (size_t)nlev * 8 : outs[k].bytes_per_col), st[i]));
+        void* q; XC_CUDA(pool_alloc(&q, (size_t)chunk * (outs[k].is3d ? (size_t)nlev : 1) * outs[k].bytes_per_col, st[i]));
         b[i].out.push_back(q);
         void* h = nullptr;
         if (staged[k]) {
@@ -567,7 +568,7 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
       if (trace) mark(&tl.back().e[2], s);
       for (size_t k = 0; k < outs.size(); ++k) {
         if (!outs[k].host) continue;
-        if (outs[k].is3d) XC_CUDA(d2h_field(outs[k].host, b[i].out[k], layout, ncol, nlev, c0, n, 8, s));
+        if (outs[k].is3d) XC_CUDA(d2h_field(outs[k].host, b[i].out[k], layout, ncol, nlev, c0, n, outs[k].bytes_per_col, s));
         else if (staged[k]) XC_CUDA(cudaMemcpyAsync(stage[i][k], b[i].out[k], (size_t)n * outs[k].bytes_per_col, cudaMemcpyDeviceToHost, s));
         else XC_CUDA(cudaMemcpyAsync((char*)outs[k].host + (size_t)c0 * outs[k].bytes_per_col, b[i].out[k], (size_t)n * outs[k].bytes_per_col, cudaMemcpyDeviceToHost, s));
       }
@@ -792,11 +793,32 @@ int xcape_cuda_stdheight(const void* p, const void* t, const void* td, const voi
   if (!p_is_1d) in3.push_back({p});
   std::vector<HostIn1> in1 = {{ps, es}, {ts, es}, {tds, es}};
   if (start_3d) in1.push_back({start_3d, 4});
-  std::vector<HostOut> outs = {{h, 0, 1}, {hs, 8, 0}};
+  std::vector<HostOut> outs = {{h, 8, 1}, {hs, 8, 0}};
   return run_staged(ncol, nlev, base_layout(layout), es, p_is_1d ? p : nullptr, in3, in1, outs,
                     [&](Block& b, int64_t n, cudaStream_t s) {
                       return dev(p_is_1d ? b.p1d : b.in3[2], b.in3[0], b.in3[1], b.in1[0], b.in1[1], b.in1[2], n,
                                  start_3d ? (const int32_t*)b.in1[3] : nullptr, (double*)b.out[0], (double*)b.out[1], s);
+                    });
+}
+
+int xcape_cuda_dewpoint_from_q(const void* p, const void* q, int64_t ncol, int nlev, int p_is_1d, int dtype, int layout,
+                               int mem, double q_min, void* td, int device, void* stream) {
+  int rc = check_common(ncol, nlev, dtype, layout, mem);
+  if (rc) return rc;
+  if (!(q_min >= 0.0) || q_min >= 1.0) return fail(XCAPE_ERR_ARG, "q_min must lie in [0, 1)");
+  if (ncol == 0) return XCAPE_OK;
+  if (!p || !q || !td) return fail(XCAPE_ERR_ARG, "null pointer");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(XCAPE_ERR_NODEV, "cudaSetDevice failed");
+  const bool lm = base_layout(layout) == XCAPE_LEVEL_MAJOR;    // elementwise: the level ORDER is irrelevant here
+  if (mem == XCAPE_MEM_DEVICE) return launch_dewpoint(p, q, td, dtype, ncol, nlev, p_is_1d != 0, lm, q_min, (cudaStream_t)stream);
+  const size_t es = esize(dtype);
+  std::vector<HostIn3> in3 = {{q}};
+  if (!p_is_1d) in3.push_back({p});
+  std::vector<HostOut> outs = {{td, es, 1}};
+  return run_staged(ncol, nlev, base_layout(layout), es, p_is_1d ? p : nullptr, in3, {}, outs,
+                    [&](Block& b, int64_t n, cudaStream_t s) {
+                      return launch_dewpoint(p_is_1d ? b.p1d : b.in3[1], b.in3[0], b.out[0], dtype, n, nlev, p_is_1d != 0, lm, q_min, s);
                     });
 }
 
