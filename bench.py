@@ -385,6 +385,11 @@ def main():
         raise SystemExit('bench.py: no CUDA device — the CUDA path has no CPU fallback')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    numa_node = None
+    full_affinity = os.sched_getaffinity(0) if hasattr(os, 'sched_getaffinity') else None
+    if not os.environ.get('XCAPE_BENCH_NO_NUMA_BIND'):
+        from xcape_b200.sharding import bind_host_to_gpu
+        numa_node = bind_host_to_gpu(local_rank)      # before any pinned allocation of this rank
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
@@ -552,6 +557,8 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             oracle.build()
+            if full_affinity is not None:
+                os.sched_setaffinity(0, full_affinity)      # the CPU baseline gets every host core again
             nth = host_threads()
             r0, _, _ = wl.cpu_rate(d, min(ncol, 2000 * nth), nth)
             sample = int(min(ncol, max(1000 * nth, r0 * args.cpu_seconds)))
@@ -566,7 +573,8 @@ def main():
                        '(reference layout), resident in HBM', 'precision': args.precision + (' (CAPE bit-exact vs oracle SPEC arithmetic)' if args.precision == 'faithful' else
                                                      ' (FP32-pipe moist body; tolerance-level parity, MU level exact)'),
                        'l2': f'inputs {h2d / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)',
-                       'parallelism': f'{world} x independent column shards, no collective'},
+                       'parallelism': f'{world} x independent column shards, no collective',
+                       'host_numa_node_of_rank0': numa_node},
             'ms_per_step_minmedmax': [float(np.min(per_step)), float(np.median(per_step)), float(np.max(per_step))],
             'ms_each_step': [round(float(x), 3) for x in per_step],
             'clocks': clocks, 'gpu_launches': int(launches),

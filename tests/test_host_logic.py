@@ -166,3 +166,13 @@ def test_stream_pipeline_order_errors_and_early_stop(tmp_path):
     with pytest.raises(ValueError):
         list(stream_srh([steps[0]], method='cuda'))          # arity error surfaces from calc_srh
     assert threading.active_count() == before
+
+
+def test_cpulist_parsing_and_numa_binding_is_harmless_without_a_gpu():
+    from xcape_b200.sharding import bind_host_to_gpu, parse_cpulist
+    assert parse_cpulist('0-3,8,10-11\n') == {0, 1, 2, 3, 8, 10, 11}
+    assert parse_cpulist('5') == {5} and parse_cpulist('') == set()
+    import os
+    before = os.sched_getaffinity(0)
+    assert bind_host_to_gpu(0) is None            # no CUDA device here: nothing changes
+    assert os.sched_getaffinity(0) == before

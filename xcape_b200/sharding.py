@@ -47,3 +47,41 @@ def run_on_devices(fn, blocks, devices):
         t.join()
     if errs:
         raise errs[0]
+
+
+def bind_host_to_gpu(device):
+    """Restrict the calling process to the CPUs of the NUMA node ``device`` hangs off, so that the
+    pinned staging buffers it allocates afterwards (first touch) and its copy threads sit next to
+    that GPU's PCIe root — with one process per GPU on a two-socket host the H2D streams otherwise
+    cross the socket interconnect.  Returns the node number, or ``None`` when the topology is not
+    visible (containers without sysfs NUMA data, single-node hosts) and nothing was changed."""
+    import os
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device)
+        bdf = f'{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0'
+        with open(f'/sys/bus/pci/devices/{bdf}/numa_node') as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f'/sys/devices/system/node/node{node}/cpulist') as f:
+            cpus = parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        cpus = cpus & allowed
+        if not cpus or cpus == allowed:
+            return None if not cpus else node
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, AttributeError, ValueError, RuntimeError, ImportError):
+        return None
+
+
+def parse_cpulist(text):
+    """'0-3,8,10-11' -> {0, 1, 2, 3, 8, 10, 11} (sysfs cpulist format)."""
+    out = set()
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        lo, _, hi = part.partition('-')
+        out.update(range(int(lo), int(hi or lo) + 1))
+    return out
