@@ -13,6 +13,8 @@ struct MathSpec {
   static constexpr bool kFastBody = false;
   static constexpr bool kSecant = false;
   static __device__ __forceinline__ float exp(float x) { return spec_expf(x); }
+  // caller guarantees |x| <= 700 (same value as exp(x): only the range guard is dropped)
+  static __device__ __forceinline__ float exp_in_range(float x) { return __double2float_rn(spec_exp_core((double)x)); }
   static __device__ __forceinline__ float exp_small(float x) { return spec_expf_small(x); }
   static __device__ __forceinline__ float log(float x) { return spec_logf(x); }
   static __device__ __forceinline__ float pow(float x, float y) { return spec_powf(x, y); }

@@ -93,13 +93,13 @@ __constant__ double kExp2[8] = {
 // XU instructions, at 2+ dispatch cycles each, cap the faithful kernel's IPC).
 __device__ __forceinline__ double spec_exp_core(double x) {
   const double tm = __dadd_rn(__dmul_rn(x, kExp2[0]), kExp2[6]);
-  const double nd = __dadd_rn(tm, kExp2[7]);
+  const double nd = __dsub_rn(tm, kExp2[6]);   // same value as tm + (-magic): one constant fewer to load
   const int n = __double2loint(tm);          // low word of t+1.5*2^52 is rint(t) in two's complement
   double r = __fma_rn(-nd, kExp2[1], x);
   r = __fma_rn(-nd, kExp2[2], r);
   double q = kExp2[3];
   q = __fma_rn(q, r, kExp2[4]);
-  q = __fma_rn(q, r, kExp2[5]);
+  q = __fma_rn(q, r, 0.5);                      // literal: fits the instruction's 32-bit immediate
   q = __fma_rn(q, r, 1.0);
   q = __fma_rn(q, r, 1.0);
   const double s = __dmul_rn(__ldg(&kExpT[n & 127]), q);
@@ -120,9 +120,9 @@ __device__ __forceinline__ double spec_exp_small_core(double x, bool tiny) {
   }
   p = __fma_rn(p, x, kExp[10]);
   p = __fma_rn(p, x, kExp[11]);
-  p = __fma_rn(p, x, kExp[12]);
-  p = __fma_rn(p, x, kExp[13]);
-  p = __fma_rn(p, x, kExp[13]);
+  p = __fma_rn(p, x, 0.5);
+  p = __fma_rn(p, x, 1.0);
+  p = __fma_rn(p, x, 1.0);
   return p;
 }
 
@@ -176,7 +176,10 @@ __device__ __forceinline__ float spec_expf(float x) {
 // exp for arguments that are almost always tiny (|x| <= 2^-3 takes the reduction-free path)
 __device__ __forceinline__ float spec_expf_small(float x) {
   const float ax = fabsf(x);
-  if (ax <= 0.125f) return __double2float_rn(spec_exp_small_core((double)x, ax <= 0.015625f));
+  // three separate returns: written as one call with a `tiny` flag, nvcc if-converts the tiers and the
+  // usual (tiny) case pays for the three extra DFMAs of the degree-8 tier plus two selects
+  if (ax <= 0.015625f) return __double2float_rn(spec_exp_small_core((double)x, true));
+  if (ax <= 0.125f) return __double2float_rn(spec_exp_small_core((double)x, false));
   return spec_expf(x);
 }
 __device__ __forceinline__ float spec_logf(float x) {
