@@ -1,5 +1,7 @@
 """The oracle against every golden vector the reference's tests hold for the path
 (reference test/test_core.py:68-286).  CPU only."""
+import os
+
 import numpy as np
 import pytest
 
@@ -106,3 +108,19 @@ def test_contracted_oracle_is_a_small_perturbation(oracle_mod, soundings):
     b = oracle_mod.calc_cape_ref(*snd_cape_args(soundings), source='surface', pinc=100, vertical_lev='sigma',
                                  contract=True)
     assert np.abs(a[0] - b[0]).max() < 1.0
+
+
+def test_dewpoint_from_q_formula_against_the_era5_fixture():
+    """The reference ships no q -> Td routine, but its ERA5 fixture carries q next to td (unused by its tests).
+    The formula behind xcape_cuda_dewpoint_from_q (inverse of getqvs) reproduces the fixture's td wherever the
+    air is above freezing — to 0.014 K on levels, 0.008 K at the surface; below 0 degC the fixture was produced
+    with an ice / mixed-phase saturation law (differences 0.6-4.3 K), which is why the op stays 'parity unpinned'."""
+    import oracle
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_era5pl.npz'))
+    td_s = oracle.dewpoint_from_q_ref(z['surf_p'], 1e-3 * z['surf_q'], q_min=0.0)          # fixture q is in g/kg
+    assert np.abs(td_s - z['surf_td']).max() < 1e-2
+    td_l = oracle.dewpoint_from_q_ref(z['level'][None, :].astype(np.float64), 1e-3 * z['lev_q'], q_min=0.0)
+    d = np.abs(td_l - z['lev_td'])
+    warm = z['lev_t'] >= 0.0
+    assert warm.sum() > 200 and d[warm].max() < 2e-2
+    assert d[~warm].min() > 0.5 and d.max() < 4.5
