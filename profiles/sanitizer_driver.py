@@ -28,5 +28,27 @@ for cfg, vlev in (('C2', 'pressure'), ('C3', 'sigma')):
     p2 = d['p'] if vlev == 'pressure' else d['p'].T
     H, Hs = stdheight(p2, d['t'].T, d['td'].T, d['ps'], d['ts'], d['tds'], 1 if vlev == 'pressure' else 0, None if vlev == 'pressure' else 1, 2., 2 if vlev == 'pressure' else 1)
     srh_two_call(d['u'].T, d['v'].T, H, d['us'], d['vs'], Hs, 1, 3000, 1, 2)
+    # level axis stored top first (negative level strides / flipped relayout / flipped 1-D pressure axis)
+    flip = lambda a: np.ascontiguousarray(a[..., ::-1])
+    fa = tuple(flip(d[k]) for k in ('p', 't', 'td', 'u', 'v'))
+    surf = (d['ps'], d['ts'], d['tds'])
+    for dt in (np.float32, np.float64):
+        c = lambda xs: [np.asarray(x, dtype=dt) for x in xs]
+        core.calc_cape(*c(fa[:3] + surf), source='most-unstable', vertical_lev=vlev, level_order='top_first')
+        lm = [fa[0] if vlev == 'pressure' else np.ascontiguousarray(fa[0].T)] + [np.ascontiguousarray(x.T) for x in fa[1:]]
+        core.calc_cape(*c(lm[:3] + list(surf)), source='mixed-layer', vertical_lev=vlev, level_order='auto', lev_axis=0)
+        core.calc_srh(*c(list(fa) + list(surf) + [d['us'], d['vs']]), vertical_lev=vlev, level_order='top_first', output_var='all')
+        core.calc_srh(*c(lm + list(surf) + [d['us'], d['vs']]), vertical_lev=vlev, level_order='top_first', lev_axis=0)
+    core.calc_cape(*(torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (lm[0], lm[1], lm[2]) + surf), source='surface',
+                   vertical_lev=vlev, level_order='top_first', lev_axis=0)
+    stdheight(fa[0] if vlev == 'pressure' else fa[0].T, fa[1].T, fa[2].T, *surf, 1 if vlev == 'pressure' else 0, None, 2.,
+              2 if vlev == 'pressure' else 1, top_first=True)
+    # q -> Td
+    from xcape_b200.thermo import dewpoint_from_q
+    q = np.full_like(d['t'], 5e-3)
+    dewpoint_from_q(d['p'], q)
+    dewpoint_from_q(d['p'] if vlev == 'pressure' else np.ascontiguousarray(d['p'].T), np.ascontiguousarray(q.T), lev_axis=0)
+    dewpoint_from_q(torch.from_numpy(d['p']).cuda() if vlev == 'pressure' else torch.from_numpy(d['p']).cuda(),
+                    torch.from_numpy(q).cuda())
 torch.cuda.synchronize()
 print('sanitizer driver done')
