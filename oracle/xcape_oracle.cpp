@@ -128,35 +128,165 @@ XC_FMA_TARGET inline double spec_exp_small_d(double x, bool tiny) {
   return p;
 }
 
-// natural log of a positive, finite, NORMAL binary64 (every positive finite
-// binary32 converts to one).
+// natural log of a positive, finite, NORMAL binary64 (every positive finite binary32 converts to one).
+// Table-driven: x = 2^k z with z in [0.6875, 1.375) cut into 128 intervals (2^-8 wide below 1, 2^-7 above);
+// per interval invc ~ 1/c (c = centre; c = 1 for the two intervals that touch 1, so that nothing cancels near
+// log(x) = 0) and logc = log(1/invc) for that ROUNDED invc, both correctly rounded from 80-digit arithmetic;
+//   r = fma(z, invc, -1)  (|r| <= 2^-7),  log1p(r) by its degree-7 Taylor polynomial (truncation < 2^-52 |r|),
+//   log x = (k ln2_hi + logc) + (k ln2_lo + log1p(r)).
+struct SpLogTab { double invc, logc; };
+static const SpLogTab SP_LOG_T[128] = {
+    {0x1.734f0c541fe8dp+0, -0x1.7cc7f7db46a0ep-2},
+    {0x1.713786d9c7c09p+0, -0x1.76feecb947176p-2},
+    {0x1.6f26016f26017p+0, -0x1.713e33a46a17cp-2},
+    {0x1.6d1a62681c861p+0, -0x1.6b85b4cffa3fdp-2},
+    {0x1.6b1490aa31a3dp+0, -0x1.65d558d4ce00bp-2},
+    {0x1.691473a88d0c0p+0, -0x1.602d08af091ecp-2},
+    {0x1.6719f3601671ap+0, -0x1.5a8cadbbedfa1p-2},
+    {0x1.6524f853b4aa3p+0, -0x1.54f431b7be1a8p-2},
+    {0x1.63356b88ac0dep+0, -0x1.4f637ebba9810p-2},
+    {0x1.614b36831ae94p+0, -0x1.49da7f3bcc420p-2},
+    {0x1.5f66434292dfcp+0, -0x1.44591e0539f49p-2},
+    {0x1.5d867c3ece2a5p+0, -0x1.3edf463c1683ep-2},
+    {0x1.5babcc647fa91p+0, -0x1.396ce359bbf53p-2},
+    {0x1.59d61f123ccaap+0, -0x1.3401e12aecba0p-2},
+    {0x1.5805601580560p+0, -0x1.2e9e2bce12286p-2},
+    {0x1.56397ba7c52e2p+0, -0x1.2941afb186b7cp-2},
+    {0x1.54725e6bb82fep+0, -0x1.23ec5991eba49p-2},
+    {0x1.52aff56a8054bp+0, -0x1.1e9e1678899f5p-2},
+    {0x1.50f22e111c4c5p+0, -0x1.1956d3b9bc2f9p-2},
+    {0x1.4f38f62dd4c9bp+0, -0x1.14167ef367784p-2},
+    {0x1.4d843bedc2c4cp+0, -0x1.0edd060b78082p-2},
+    {0x1.4bd3edda68fe1p+0, -0x1.09aa572e6c6d4p-2},
+    {0x1.4a27fad76014ap+0, -0x1.047e60cde83b7p-2},
+    {0x1.4880522014880p+0, -0x1.feb2233ea07cbp-3},
+    {0x1.46dce34596066p+0, -0x1.f474b134df228p-3},
+    {0x1.453d9e2c776cap+0, -0x1.ea4449f04aaf5p-3},
+    {0x1.43a2730abee4dp+0, -0x1.e020cc6235ab5p-3},
+    {0x1.420b5265e5951p+0, -0x1.d60a17f903514p-3},
+    {0x1.40782d10e6566p+0, -0x1.cc000c9db3c52p-3},
+    {0x1.3ee8f42a5af07p+0, -0x1.c2028ab17f9b5p-3},
+    {0x1.3d5d991aa75c6p+0, -0x1.b811730b823d4p-3},
+    {0x1.3bd60d9232955p+0, -0x1.ae2ca6f672bd8p-3},
+    {0x1.3a524387ac822p+0, -0x1.a454082e6ab03p-3},
+    {0x1.38d22d366088ep+0, -0x1.9a8778debaa3ap-3},
+    {0x1.3755bd1c945eep+0, -0x1.90c6db9fcbcdbp-3},
+    {0x1.35dce5f9f2af8p+0, -0x1.871213750e994p-3},
+    {0x1.34679ace01346p+0, -0x1.7d6903caf5acdp-3},
+    {0x1.32f5ced6a1dfap+0, -0x1.73cb9074fd14dp-3},
+    {0x1.3187758e9ebb6p+0, -0x1.6a399dabbd383p-3},
+    {0x1.301c82ac40260p+0, -0x1.60b3100b09474p-3},
+    {0x1.2eb4ea1fed14bp+0, -0x1.5737cc9018cddp-3},
+    {0x1.2d50a012d50a0p+0, -0x1.4dc7b897bc1c7p-3},
+    {0x1.2bef98e5a3711p+0, -0x1.4462b9dc9b3dcp-3},
+    {0x1.2a91c92f3c105p+0, -0x1.3b08b6757f2a7p-3},
+    {0x1.293725bb804a5p+0, -0x1.31b994d3a4f86p-3},
+    {0x1.27dfa38a1ce4dp+0, -0x1.28753bc11aba2p-3},
+    {0x1.268b37cd60127p+0, -0x1.1f3b925f25d44p-3},
+    {0x1.2539d7e9177b2p+0, -0x1.160c8024b27b0p-3},
+    {0x1.23eb79717605bp+0, -0x1.0ce7ecdccc28bp-3},
+    {0x1.22a0122a0122ap+0, -0x1.03cdc0a51ec0dp-3},
+    {0x1.21579804855e6p+0, -0x1.f57bc7d9005dbp-4},
+    {0x1.2012012012012p+0, -0x1.e3707ee30487bp-4},
+    {0x1.1ecf43c7fb84cp+0, -0x1.d179788219362p-4},
+    {0x1.1d8f5672e4abdp+0, -0x1.bf968769fca18p-4},
+    {0x1.1c522fc1ce059p+0, -0x1.adc77ee5aea8ep-4},
+    {0x1.1b17c67f2bae3p+0, -0x1.9c0c32d4d254dp-4},
+    {0x1.19e0119e0119ep+0, -0x1.8a6477a91dc29p-4},
+    {0x1.18ab083902bdbp+0, -0x1.78d02263d82d7p-4},
+    {0x1.1778a191bd684p+0, -0x1.674f089365a78p-4},
+    {0x1.1648d50fc3201p+0, -0x1.55e10050e0382p-4},
+    {0x1.151b9a3fdd5c9p+0, -0x1.4485e03dbdfb0p-4},
+    {0x1.13f0e8d344724p+0, -0x1.333d7f8183f4ap-4},
+    {0x1.12c8b89edc0acp+0, -0x1.2207b5c7854a1p-4},
+    {0x1.11a3019a74826p+0, -0x1.10e45b3cae829p-4},
+    {0x1.107fbbe011080p+0, -0x1.ffa6911ab9309p-5},
+    {0x1.0f5edfab325a2p+0, -0x1.dda8adc67ee59p-5},
+    {0x1.0e40655826011p+0, -0x1.bbcebfc68f424p-5},
+    {0x1.0d24456359e3ap+0, -0x1.9a187b573de81p-5},
+    {0x1.0c0a7868b4171p+0, -0x1.788595a3577c8p-5},
+    {0x1.0af2f722eecb5p+0, -0x1.5715c4c03cee1p-5},
+    {0x1.09ddba6af8360p+0, -0x1.35c8bfaa13069p-5},
+    {0x1.08cabb37565e2p+0, -0x1.149e3e4005a8dp-5},
+    {0x1.07b9f29b8eae2p+0, -0x1.e72bf2813ce6ap-6},
+    {0x1.06ab59c7912fbp+0, -0x1.a55f548c5c427p-6},
+    {0x1.059eea0727586p+0, -0x1.63d6178690bbep-6},
+    {0x1.04949cc1664c5p+0, -0x1.228fb1fea2e0ap-6},
+    {0x1.038c6b78247fcp+0, -0x1.c317384c75f0dp-7},
+    {0x1.02864fc7729e9p+0, -0x1.41929f968330cp-7},
+    {0x1.0182436517a37p+0, -0x1.8121214586b02p-8},
+    {0x1.0000000000000p+0, 0x0.0p+0},
+    {0x1.0000000000000p+0, 0x0.0p+0},
+    {0x1.fa11caa01fa12p-1, 0x1.7dc475f810a69p-7},
+    {0x1.f6310aca0dbb5p-1, 0x1.3cea44346a584p-6},
+    {0x1.f25f644230ab5p-1, 0x1.b9fc027af919ap-6},
+    {0x1.ee9c7f8458e02p-1, 0x1.1b0d98923d97fp-5},
+    {0x1.eae807aba01ebp-1, 0x1.58a5bafc8e4d3p-5},
+    {0x1.e741aa59750e4p-1, 0x1.95c830ec8e3f2p-5},
+    {0x1.e3a9179dc1a73p-1, 0x1.d276b8adb0b56p-5},
+    {0x1.e01e01e01e01ep-1, 0x1.075983598e471p-4},
+    {0x1.dca01dca01dcap-1, 0x1.253f62f0a1417p-4},
+    {0x1.d92f2231e7f8ap-1, 0x1.42edcbea646eep-4},
+    {0x1.d5cac807572b2p-1, 0x1.60658a93750c4p-4},
+    {0x1.d272ca3fc5b1ap-1, 0x1.7da766d7b12d0p-4},
+    {0x1.cf26e5c44bfc6p-1, 0x1.9ab42462033aep-4},
+    {0x1.cbe6d9601cbe7p-1, 0x1.b78c82bb0eda0p-4},
+    {0x1.c8b265afb8a42p-1, 0x1.d4313d66cb35dp-4},
+    {0x1.c5894d10d4986p-1, 0x1.f0a30c01162a4p-4},
+    {0x1.c26b5392ea01cp-1, 0x1.0671512ca596fp-3},
+    {0x1.bf583ee868d8bp-1, 0x1.14785846742acp-3},
+    {0x1.bc4fd65883e7bp-1, 0x1.2266f190a5acdp-3},
+    {0x1.b951e2b18ff23p-1, 0x1.303d718e47fd5p-3},
+    {0x1.b65e2e3beee05p-1, 0x1.3dfc2b0ecc62ap-3},
+    {0x1.b37484ad806cep-1, 0x1.4ba36f39a55e5p-3},
+    {0x1.b094b31d922a4p-1, 0x1.59338d9982085p-3},
+    {0x1.adbe87f94905ep-1, 0x1.66acd4272ad51p-3},
+    {0x1.aaf1d2f87ebfdp-1, 0x1.740f8f54037a3p-3},
+    {0x1.a82e65130e159p-1, 0x1.815c0a14357e9p-3},
+    {0x1.a574107688a4ap-1, 0x1.8e928de886d41p-3},
+    {0x1.a2c2a87c51ca0p-1, 0x1.9bb362e7dfb85p-3},
+    {0x1.a01a01a01a01ap-1, 0x1.a8becfc882f19p-3},
+    {0x1.9d79f176b682dp-1, 0x1.b5b519e8fb5a6p-3},
+    {0x1.9ae24ea5510dap-1, 0x1.c2968558c18c2p-3},
+    {0x1.9852f0d8ec0ffp-1, 0x1.cf6354e09c5ddp-3},
+    {0x1.95cbb0be377aep-1, 0x1.dc1bca0abec7bp-3},
+    {0x1.934c67f9b2ce6p-1, 0x1.e8c0252aa5a60p-3},
+    {0x1.90d4f120190d5p-1, 0x1.f550a564b7b37p-3},
+    {0x1.8e6527af1373fp-1, 0x1.00e6c45ad501dp-2},
+    {0x1.8bfce8062ff3ap-1, 0x1.071b85fcd590dp-2},
+    {0x1.899c0f601899cp-1, 0x1.0d46b579ab74bp-2},
+    {0x1.87427bcc092b9p-1, 0x1.136870293a8b0p-2},
+    {0x1.84f00c2780614p-1, 0x1.1980d2dd4236fp-2},
+    {0x1.82a4a0182a4a0p-1, 0x1.1f8ff9e48a2f3p-2},
+    {0x1.8060180601806p-1, 0x1.2596010df763ap-2},
+    {0x1.7e225515a4f1dp-1, 0x1.2b9303ab89d25p-2},
+    {0x1.7beb3922e017cp-1, 0x1.31871c9544185p-2},
+    {0x1.79baa6bb6398bp-1, 0x1.3772662bfd85cp-2},
+    {0x1.77908119ac60dp-1, 0x1.3d54fa5c1f710p-2},
+    {0x1.756cac201756dp-1, 0x1.432ef2a04e813p-2},
+};
+
 XC_FMA_TARGET inline double spec_log_d(double x) {
   if (!(x > 0.0)) return (x == 0.0) ? -INFINITY : NAN;
   if (x == INFINITY) return x;
-  uint64_t b = d2bits(x);
-  int64_t e = (int64_t)(b >> 52) - 1023;
-  double m = bits2d((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);  // [1,2)
-  if (m > 0x1.6a09e667f3bcdp+0) { m = m * 0.5; e += 1; }                  // (sqrt.5, sqrt2]
-  double f = m - 1.0;
-  double d = m + 1.0;
-  double y = __builtin_fma(-0.2391, d, 0.98525);   // linear seed for 1/d on [1.707, 2.414]
-  double t = __builtin_fma(-d, y, 1.0); y = __builtin_fma(y, t, y);
-  t = __builtin_fma(-d, y, 1.0); y = __builtin_fma(y, t, y);
-  t = __builtin_fma(-d, y, 1.0); y = __builtin_fma(y, t, y);
-  double s = f * y;
-  double z = s * s;
-  double q = 0x1.1111111111111p-4;                 // 1/15
-  q = __builtin_fma(q, z, 0x1.3b13b13b13b14p-4);   // 1/13
-  q = __builtin_fma(q, z, 0x1.745d1745d1746p-4);   // 1/11
-  q = __builtin_fma(q, z, 0x1.c71c71c71c71cp-4);   // 1/9
-  q = __builtin_fma(q, z, 0x1.2492492492492p-3);   // 1/7
-  q = __builtin_fma(q, z, 0x1.999999999999ap-3);   // 1/5
-  q = __builtin_fma(q, z, 0x1.5555555555555p-2);   // 1/3
-  q = __builtin_fma(q, z, 1.0);
-  double lm = (s + s) * q;
-  double ed = (double)e;
-  double r = __builtin_fma(ed, SP_LN2_LO, lm);
-  return __builtin_fma(ed, SP_LN2_HI, r);
+  const uint64_t ix = d2bits(x);
+  const uint64_t tmp = ix - 0x3fe6000000000000ULL;
+  const int i = (int)((tmp >> 45) & 127);
+  const int64_t k = (int64_t)tmp >> 52;                                     // arithmetic shift
+  const double z = bits2d(ix - (tmp & 0xfff0000000000000ULL));
+  const double r = __builtin_fma(z, SP_LOG_T[i].invc, -1.0);
+  const double kd = (double)k;
+  double q = 0x1.2492492492492p-3;                  //  1/7
+  q = __builtin_fma(q, r, -0x1.5555555555555p-3);   // -1/6
+  q = __builtin_fma(q, r, 0x1.999999999999ap-3);    //  1/5
+  q = __builtin_fma(q, r, -0.25);
+  q = __builtin_fma(q, r, 0x1.5555555555555p-2);    //  1/3
+  q = __builtin_fma(q, r, -0.5);
+  const double r2 = r * r;
+  const double lp = __builtin_fma(q, r2, r);        // log1p(r)
+  const double hi = __builtin_fma(kd, SP_LN2_HI, SP_LOG_T[i].logc);
+  const double lo = __builtin_fma(kd, SP_LN2_LO, lp);
+  return hi + lo;
 }
 
 enum { T_LIBM = 0, T_CR = 1, T_SPEC = 2 };
