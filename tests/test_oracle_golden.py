@@ -73,6 +73,10 @@ def test_stdheight_golden(oracle_mod, soundings):
     assert np.array_equal(Hs, ref[:, 0])
 
 
+def L_one(oracle_mod):
+    return float(oracle_mod.lib().xcape_ref_logf(1.0, 2))
+
+
 def test_spec_math_is_a_valid_libm(oracle_mod):
     """SPEC exp/log/pow agree with the correctly-rounded binary32 result."""
     rng = np.random.default_rng(0)
@@ -84,6 +88,18 @@ def test_spec_math_is_a_valid_libm(oracle_mod):
     assert (oracle_mod.vec_math('exp_small', x, tmode=2) != oracle_mod.vec_math('exp', x, tmode=1)).mean() < 1e-4
     x = np.exp(rng.uniform(-8, 8, 500_000)).astype(np.float32)
     assert (oracle_mod.vec_math('log', x, tmode=2) != oracle_mod.vec_math('log', x, tmode=1)).mean() < 1e-4
+    # the table-driven log near its cancellation-prone spot: EVERY binary32 within 2^-10 of 1, the interval
+    # edges of the table, and pressure ratios p2/p1 of the ascent
+    lo, hi = np.float32(1 - 2.0 ** -10).view(np.uint32), np.float32(1 + 2.0 ** -10).view(np.uint32)
+    x = np.arange(lo, hi + 1, dtype=np.uint32).view(np.float32)
+    assert (oracle_mod.vec_math('log', x, tmode=2) != oracle_mod.vec_math('log', x, tmode=1)).sum() == 0
+    edges = np.float32(0.6875) + np.arange(0, 176, dtype=np.float32) * np.float32(2.0 ** -8)     # 0.6875 .. 1.375
+    x = np.concatenate([np.nextafter(edges, np.float32(0)), edges, np.nextafter(edges, np.float32(2))]).astype(np.float32)
+    x = np.concatenate([x * np.float32(2.0 ** k) for k in (-126, -20, -1, 0, 1, 30, 126)])
+    assert (oracle_mod.vec_math('log', x, tmode=2) != oracle_mod.vec_math('log', x, tmode=1)).sum() == 0
+    x = rng.uniform(0.9, 1.0, 500_000).astype(np.float32)
+    assert (oracle_mod.vec_math('log', x, tmode=2) != oracle_mod.vec_math('log', x, tmode=1)).mean() < 1e-4
+    assert L_one(oracle_mod) == 0.0
     x = rng.uniform(0.0005, 1.1, 500_000).astype(np.float32)
     y = np.float32(287.04) / np.float32(1005.7)
     assert (oracle_mod.vec_math('pow', x, y, tmode=2) != oracle_mod.vec_math('pow', x, y, tmode=1)).mean() < 1e-4
