@@ -876,3 +876,39 @@ def test_dewpoint_from_q(oracle_mod):
     assert not np.isfinite(dewpoint_from_q(e['p'], z, q_min=0.0)).any()
     with pytest.raises(ValueError):
         dewpoint_from_q(e['p'][:5], q2)
+
+
+def test_every_output_element_is_written(core, monkeypatch):
+    """Host outputs are handed to the library uninitialised (np.empty).  With XCAPE_B200_POISON_OUTPUTS they are
+    pre-filled with a sentinel instead: after calls that cover gated, NaN, non-converging, garbage and
+    work-list (non-monotone) columns, ragged block sizes and every output of every entry point, no sentinel
+    may be left."""
+    from xcape_b200 import _array as A
+    from xcape_b200.stdheight_cuda import stdheight
+    from xcape_b200.synthetic import make_soundings
+    from xcape_b200.thermo import dewpoint_from_q
+    monkeypatch.setenv('XCAPE_B200_POISON_OUTPUTS', '1')
+    monkeypatch.setenv('XCAPE_B200_CHUNK_COLS', '8192')
+    monkeypatch.setenv('XCAPE_B200_FIRST_CHUNK_COLS', '2048')
+    clean = lambda outs: all(not (np.asarray(o) == A.POISON).any() for o in outs)
+    for cfg, vlev in (('C3', 'sigma'), ('C2', 'pressure')):
+        d = make_soundings(cfg, cols=(0, 20_000 + 77), active=False, winds=True)          # ~45 % gated columns
+        p, t, td = d['p'].copy(), d['t'].copy(), d['td'].copy()
+        ts, tds = d['ts'].copy(), d['tds'].copy()
+        ts[5::97] = np.nan; t[7::101, 3] = np.nan; td[11::103, :] = 1e30                 # NaN gate, NaN level, garbage
+        ts[13::107] = 45.0; tds[13::107] = 44.0                                          # hot, moist: non-convergence candidates
+        if vlev == 'sigma':
+            p[17::109, 9] = p[17::109, 8]                                                # non-monotone pressure: SRH work list
+        for src in ('surface', 'most-unstable', 'mixed-layer'):
+            for prec in ('faithful', 'fast'):
+                assert clean(core.calc_cape(p, t, td, d['ps'], ts, tds, source=src, vertical_lev=vlev, precision=prec))
+        from xcape_b200.cape_cuda import cape
+        p2 = p if vlev == 'pressure' else p.T
+        assert clean(cape(p2, t.T, td.T, d['ps'], ts, tds, int(vlev == 'pressure'), None, 2, 500., 1, 500.,
+                          2 if vlev == 'pressure' else 1, return_counters=True))
+        for prec in ('faithful', 'fast'):
+            assert clean(core.calc_srh(p, t, td, d['u'], d['v'], d['ps'], ts, tds, d['us'], d['vs'], vertical_lev=vlev,
+                                       output_var='all', precision=prec))
+        assert clean(stdheight(p2, t.T, td.T, d['ps'], ts, tds, int(vlev == 'pressure'), None, 2., 2 if vlev == 'pressure' else 1))
+        q = np.full_like(t, 4e-3)
+        assert clean([dewpoint_from_q(d['p'], q)])

@@ -1,9 +1,14 @@
 """Array plumbing shared by the CUDA shims: numpy arrays (host memory) and torch tensors
 (host, or CUDA device memory passed zero-copy as raw pointers).  torch is optional and is
 only ever used for memory / streams — never for arithmetic on the product path."""
+import os
+
 import numpy as np
 
 from . import _lib
+
+
+POISON = -12345          # sentinel of XCAPE_B200_POISON_OUTPUTS (exact in float32 / float64 / int32)
 
 
 def is_torch(a):
@@ -78,11 +83,15 @@ def ptr(a):
 
 
 def empty_like_host_or_device(ref, shape, dtype):
-    """Output buffer living where ``ref`` lives."""
+    """Output buffer living where ``ref`` lives.  Uninitialised on purpose: the library writes every element
+    of every output it is handed (gated, abandoned and work-list columns included), and zero-filling the four
+    4 MB results of an ERA5 field cost 0.5 ms of a 14 ms call."""
     if is_cuda(ref):
         import torch
         return torch.empty(shape, dtype=getattr(torch, dtype), device=ref.device)
-    return np.zeros(shape, dtype=dtype)
+    if os.environ.get('XCAPE_B200_POISON_OUTPUTS'):       # tests: prove that nothing is left unwritten
+        return np.full(shape, POISON, dtype=dtype)
+    return np.empty(shape, dtype=dtype)
 
 
 def stream_of(ref, stream=None):
