@@ -109,25 +109,6 @@ XC_FMA_TARGET inline double spec_exp_d(double x) {
   return bits2d(d2bits(s) + ((uint64_t)(n >> 7) << 52));
 }
 
-// |x| <= 2^-3: no range reduction; |x| <= 2^-6: Taylor degree 5, else degree 8
-XC_FMA_TARGET inline double spec_exp_small_d(double x, bool tiny) {
-  double p;
-  if (tiny) {
-    p = 0x1.1111111111111p-7;                          // 1/5!
-  } else {
-    p = 0x1.a01a01a01a01ap-16;                         // 1/8!
-    p = __builtin_fma(p, x, 0x1.a01a01a01a01ap-13);    // 1/7!
-    p = __builtin_fma(p, x, 0x1.6c16c16c16c17p-10);    // 1/6!
-    p = __builtin_fma(p, x, 0x1.1111111111111p-7);     // 1/5!
-  }
-  p = __builtin_fma(p, x, 0x1.5555555555555p-5);       // 1/4!
-  p = __builtin_fma(p, x, 0x1.5555555555555p-3);       // 1/3!
-  p = __builtin_fma(p, x, 0.5);
-  p = __builtin_fma(p, x, 1.0);
-  p = __builtin_fma(p, x, 1.0);
-  return p;
-}
-
 // natural log of a positive, finite, NORMAL binary64 (every positive finite binary32 converts to one).
 // Table-driven: x = 2^k z with z in [0.6875, 1.375) cut into 128 intervals (2^-8 wide below 1, 2^-7 above);
 // per interval invc ~ 1/c (c = centre; c = 1 for the two intervals that touch 1, so that nothing cancels near
@@ -289,16 +270,67 @@ XC_FMA_TARGET inline double spec_log_d(double x) {
   return hi + lo;
 }
 
+// ---------------------------------------------------------------------------
+// SPEC exp32: the binary32 exp of SPEC mode (DESIGN.md §SPEC math).  Float-float tails, only IEEE
+// binary32 +, -, *, fma and integer operations; written here independently of the CUDA version
+// (xcape_b200/csrc/xc_math_spec.cuh), with which it agrees bit for bit by construction.
+//   t = fma(x, 1024 log2e, 1.5*2^23)  ->  n = rint(1024 x log2e) in t's low mantissa bits
+//   r = x - n ln2/1024 (two fmas, the first exact);  p = r + r^2 (1/2 + r/6)
+//   exp(x) = 2^(n div 1024) * (Th + fma(Th, p, Tl)),  {Th, Tl} = 2^((n mod 1024)/1024) as a binary32 pair
+// ---------------------------------------------------------------------------
+struct SpF2 { float hi, lo; };
+static const SpF2 SP_EXP32_T[1024] = {
+#include "xc_exp32_table.inc"
+};
+inline int32_t f2bits(float f) { int32_t i; std::memcpy(&i, &f, 4); return i; }
+inline float bits2f(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
+
+XC_FMA_TARGET inline float spec32_exp_mant(float x, int32_t& n) {
+  const float t = __builtin_fmaf(x, 0x1.715476p+10f, 12582912.0f);
+  const float nf = t - 12582912.0f;
+  float r = __builtin_fmaf(nf, -0x1.62e43p-11f, x);
+  r = __builtin_fmaf(nf, 0x1.05c61p-39f, r);
+  const int32_t bt = f2bits(t);
+  const SpF2 T = SP_EXP32_T[bt & 1023];
+  const float q = __builtin_fmaf(r, 0x1.555556p-3f, 0.5f);
+  const float v = r * r;
+  const float p = __builtin_fmaf(q, v, r);
+  const float s = __builtin_fmaf(T.hi, p, T.lo);
+  n = bt - 0x4B400000;
+  return T.hi + s;
+}
+XC_FMA_TARGET inline float spec32_expf(float x) {
+  if (x != x) return x;
+  if (x > 88.72283172607421875f) return INFINITY;             // largest binary32 whose exp is finite
+  if (x < -104.0f) return 0.0f;
+  int32_t n;
+  const float y = spec32_exp_mant(x, n);
+  const int32_t e = n >> 10;                                   // floor division
+  if (x >= -87.0f) return bits2f(f2bits(y) + e * (1 << 23));   // normal result (e >= -126)
+  const float big = bits2f(f2bits(y) + (e + 64) * (1 << 23));  // subnormal range: one rounding, in the last product
+  return big * 0x1p-64f;
+}
+// |x| <= 2^-6: 1 + x = h + e exactly, Taylor tail joins e, one final rounding
+XC_FMA_TARGET inline float spec32_exp_tiny(float x) {
+  const float h = 1.0f + x;
+  const float e = x - (h - 1.0f);
+  const float v = x * x;
+  float u = __builtin_fmaf(x, 0x1.111112p-7f, 0x1.555556p-5f);
+  u = __builtin_fmaf(u, x, 0x1.555556p-3f);
+  u = __builtin_fmaf(u, x, 0.5f);
+  return h + __builtin_fmaf(v, u, e);
+}
+
 enum { T_LIBM = 0, T_CR = 1, T_SPEC = 2 };
 
 template <int TM> inline float t_exp(float x) {
   if (TM == T_LIBM) return expf(x);
   if (TM == T_CR) return (float)exp((double)x);
-  return (float)spec_exp_d((double)x);
+  return spec32_expf(x);
 }
 // exp for the theta2 update (f90:460-462), whose argument is almost always tiny
 template <int TM> inline float t_exp_small(float x) {
-  if (TM == T_SPEC && std::fabs(x) <= 0.125f) return (float)spec_exp_small_d((double)x, std::fabs(x) <= 0.015625f);
+  if (TM == T_SPEC && std::fabs(x) <= 0.015625f) return spec32_exp_tiny(x);
   return t_exp<TM>(x);
 }
 template <int TM> inline float t_log(float x) {
@@ -351,6 +383,13 @@ template <int TM> inline float getthe(float p, float t, float td, float q) {   /
 }
 
 struct ColOut { float cape, cin, zout; int32_t mulvl; int32_t n_iter, n_sub, status; };
+
+// Diagnostic trace (profiles/divergence_model.py): per column, a list of int16 — for every layer of the ascent
+// -(1000 + k), -nloop, then the number of moist passes of each of its sub-steps.  Used to model what a SIMT warp pays for
+// lanes that need different pass counts; not part of any parity check.
+thread_local int16_t* g_trace = nullptr;
+thread_local int g_trace_cap = 0, g_trace_n = 0;
+inline void trace_put(int v) { if (g_trace && g_trace_n < g_trace_cap) g_trace[g_trace_n++] = (int16_t)v; }
 enum { ST_OK = 0, ST_SKIPPED = 1, ST_NONCONV = 2 };
 constexpr int NLOOP_CAP = 1 << 16;     // sub-steps per layer beyond this, or a NaN step => status 3 (invalid sounding)
 constexpr int ITER_BUDGET = 1 << 22;   // moist passes per column beyond this => status 3
@@ -474,6 +513,7 @@ void getcape(const float* pA, const float* tA, const float* tdA, int64_t ls_p, i
       nloop = 1 + (int)r;
       dp = dp / (float)nloop;
     }
+    trace_put(-(1000 + k)); trace_put(-nloop);                    // k: index of the layer's upper level in the assembled column
     for (int n = 1; n <= nloop; ++n) {
       float p1 = p2, t1 = t2, th1 = th2, qv1 = qv2, ql1 = ql2, qi1 = qi2;
       p2 = p2 - dp;
@@ -511,6 +551,7 @@ void getcape(const float* pA, const float* tA, const float* tdA, int64_t ls_p, i
         if (std::fabs(th2 - thlast) > c_converge) thlast = thlast + 0.3f * (th2 - thlast);
         else not_converged = false;
       }
+      trace_put(i);
       if (o.n_iter > ITER_BUDGET) { o.cape = 0.0f; o.cin = 0.0f; o.status = ST_INVALID; return; }
       if (pseudo) { qt = qv2; ql2 = 0.0f; qi2 = 0.0f; }          // f90:487-491
     }
@@ -717,6 +758,24 @@ int xcape_ref_loopcape_pl1d(const float* t3d, const float* td3d, const float* p1
     else if (tmode == T_CR) loopcape_range<T_CR>(a, b, p1d, t3d, td3d, true, ps, ts, tds, pinc, source, ml_depth, adiabat, start_3d, nk, cape, cin, mulvl, zout, n_iter, n_sub, status);
     else loopcape_range<T_SPEC>(a, b, p1d, t3d, td3d, true, ps, ts, tds, pinc, source, ml_depth, adiabat, start_3d, nk, cape, cin, mulvl, zout, n_iter, n_sub, status);
   });
+  return 0;
+}
+
+// diagnostic: loopcape_pl1d / loopcape_ml (SPEC arithmetic, one thread) with the per-sub-step pass counts of every
+// column written to trace[i*cap .. ) (see g_trace above; unused slots stay 0)
+int xcape_ref_cape_trace(const float* p, const float* t3d, const float* td3d, int p_is_1d, const float* ps,
+                         const float* ts, const float* tds, float pinc, int source, float ml_depth, int adiabat,
+                         const int32_t* start_3d, int nk, int64_t n2, int16_t* trace, int cap) {
+  if (source < 1 || source > 3 || adiabat < 1 || adiabat > 4 || !(pinc > 0.0f) || nk < 1) return 1;
+  std::vector<float> cape(1), cin(1), zout(1);
+  std::vector<int32_t> mulvl(1);
+  std::memset(trace, 0, (size_t)n2 * cap * sizeof(int16_t));
+  for (int64_t i = 0; i < n2; ++i) {
+    g_trace = trace + i * cap; g_trace_cap = cap; g_trace_n = 0;
+    loopcape_range<T_SPEC>(i, i + 1, p, t3d, td3d, p_is_1d != 0, ps, ts, tds, pinc, source, ml_depth, adiabat, start_3d, nk,
+                           cape.data() - i, cin.data() - i, mulvl.data() - i, zout.data() - i, nullptr, nullptr, nullptr);
+  }
+  g_trace = nullptr;
   return 0;
 }
 

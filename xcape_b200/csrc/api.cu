@@ -11,7 +11,7 @@
 
 #include "xc_common.cuh"
 #include "relayout.cuh"
-#include "cape_kernel.cuh"
+#include "cape_args.cuh"
 #include "srh_launch.cuh"
 #include "peaks.cuh"
 #include "thermo.cuh"

@@ -1,0 +1,30 @@
+// cape_args.cuh — argument block of the CAPE kernels (shared by the launchers in api.cu and the kernel TUs).
+#pragma once
+#include <stdint.h>
+
+namespace xc {
+
+struct CapeArgs {
+  const float* __restrict__ p;     // P1D: [nlev] hPa; else level-major [nlev][ld]
+  const float* __restrict__ t;     // level-major [nlev][ld], degC
+  const float* __restrict__ td;
+  const float* __restrict__ ps;    // [ncol]
+  const float* __restrict__ ts;
+  const float* __restrict__ tds;
+  const int32_t* __restrict__ start;   // [ncol] 1-based first level used, or nullptr (=1)
+  int64_t ncol;
+  int64_t ld;                      // distance (elements) between consecutive levels
+  int nlev;
+  float pinc;
+  float ml_depth;
+  float* __restrict__ cape;
+  float* __restrict__ cin;
+  float* __restrict__ zout;
+  int32_t* __restrict__ mulvl;
+  int32_t* __restrict__ status;    // nullable
+  int32_t* __restrict__ n_iter;    // nullable: moist iterations executed (roofline work counter)
+  const float* __restrict__ pl_pi; // P1D only, nullable: Exner function of the nlev pressure levels, precomputed once per
+                                   // call by exner_table_kernel with the same SPEC pow (bit-identical, saves a pow per level)
+};
+
+}  // namespace xc

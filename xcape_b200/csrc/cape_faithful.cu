@@ -12,10 +12,20 @@ namespace xc {
 struct MathSpec {
   static constexpr bool kFastBody = false;
   static constexpr bool kSecant = false;
+#if defined(XC_EXP64)
+  // round-1 arithmetic: binary64 exp cores behind F2F conversions (kept for A/B timing only)
   static __device__ __forceinline__ float exp(float x) { return spec_expf(x); }
-  // caller guarantees |x| <= 700 (same value as exp(x): only the range guard is dropped)
   static __device__ __forceinline__ float exp_in_range(float x) { return __double2float_rn(spec_exp_core((double)x)); }
   static __device__ __forceinline__ float exp_small(float x) { return spec_expf_small(x); }
+  static __device__ __forceinline__ float exp_tiny(float x) { return __double2float_rn(spec_exp_small_core((double)x, true)); }
+#else
+  static __device__ __forceinline__ float exp(float x) { return spec32_expf(x); }
+  // caller guarantees |x| <= 88 (same value as exp(x): only the range guard is dropped)
+  static __device__ __forceinline__ float exp_in_range(float x) { return spec32_exp_core(x); }
+  // the theta update's exp (f90:460-462); exp_tiny: caller guarantees |x| <= 2^-6 (same value as exp_small(x))
+  static __device__ __forceinline__ float exp_small(float x) { return spec32_expf_small(x); }
+  static __device__ __forceinline__ float exp_tiny(float x) { return spec32_exp_tiny(x); }
+#endif
   static __device__ __forceinline__ float log(float x) { return spec_logf(x); }
   static __device__ __forceinline__ float pow(float x, float y) { return spec_powf(x, y); }
 };

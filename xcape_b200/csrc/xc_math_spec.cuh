@@ -310,6 +310,93 @@ __device__ __forceinline__ float spec_expf_small(float x) {
   if (ax <= 0.125f) return __double2float_rn(spec_exp_small_core((double)x, false));
   return spec_expf(x);
 }
+// ---- binary32 exp ("SPEC exp32"): FP32 pipe only, no conversions, no FP64 ----------------------------
+// The moist iteration evaluates exp twice per pass (Bolton's es(T), f90:570-581, and the theta update,
+// f90:460-462).  With the binary64 core each call cost two F2F conversions (XU pipe, 8 cycles per warp
+// instruction) and 10 resp. 5 FP64 instructions (2 cycles each); ncu r1u showed XU as the busiest pipe.
+// This version stays in binary32 with float-float tails:
+//   t = fma(x, 1024 log2e, 1.5*2^23); n = rint(..) sits in t's low mantissa bits; nf = t - 1.5*2^23
+//   r = fma(nf, -L2, fma(nf, -L1, x))        L1 = RN32(ln2/1024) (the inner fma is exact), L2 = RN32(ln2/1024 - L1)
+//   p = r + r^2 (1/2 + r/6)                   |r| <= 2^-11.5: the next term is < 2^-50
+//   y = Th[j] + fma(Th[j], p, Tl[j])          j = n mod 1024, {Th, Tl} = 2^(j/1024) as a binary32 pair
+//   exp(x) = y * 2^(n div 1024)               added to the exponent field
+// Pre-rounding error ~2^-11 ulp: on 5e7 arguments in [-53.6, 7.1] it differs from the correctly rounded
+// binary32 exp in 1.0e-4 of the calls, never by more than one ulp (glibc's expf: 6.2e-4) — a valid libm.
+// Only IEEE binary32 +, -, *, fma and integer operations: oracle/xcape_oracle.cpp reproduces it bit for bit.
+__device__ const float2 kExp32T[1024] = {
+#include "xc_exp32_table.inc"
+};
+namespace e32 {
+constexpr float kKL = 0x1.715476p+10f;     // RN32(1024 log2 e)
+constexpr float kL1 = 0x1.62e43p-11f;      // RN32(ln2 / 1024)
+constexpr float kL2 = -0x1.05c61p-39f;     // RN32(ln2 / 1024 - L1)
+constexpr float kMagic = 12582912.0f;      // 1.5 * 2^23
+constexpr float kC3 = 0x1.555556p-3f;      // RN32(1/6)
+}  // namespace e32
+
+// The CAPE kernels keep a copy of the table in shared memory (8 KB per CTA): the index differs per lane, and
+// LDS with a scaled index costs two instructions where the global-memory path costs five (64-bit address
+// arithmetic) plus an L1 round trip.  A kernel that uses the exp32 functions calls exp32_smem_fill() first.
+#ifndef XC_EXP32_GLOBAL_TABLE
+__shared__ float2 sExp32T[1024];
+__device__ __forceinline__ void exp32_smem_fill() {
+  for (int k = threadIdx.x; k < 1024; k += blockDim.x) sExp32T[k] = kExp32T[k];
+  __syncthreads();
+}
+__device__ __forceinline__ float2 exp32_entry(int j) { return sExp32T[j]; }
+#else
+__device__ __forceinline__ void exp32_smem_fill() {}
+__device__ __forceinline__ float2 exp32_entry(int j) { return __ldg(&kExp32T[j]); }
+#endif
+
+// y in [1, 2) and the integer n (n div 1024 = binary exponent) for |x| <= 104
+__device__ __forceinline__ float spec32_exp_mant(float x, int& n) {
+  const float t = __fmaf_rn(x, e32::kKL, e32::kMagic);
+  const float nf = __fsub_rn(t, e32::kMagic);
+  float r = __fmaf_rn(nf, -e32::kL1, x);
+  r = __fmaf_rn(nf, -e32::kL2, r);
+  const int bt = __float_as_int(t);
+  const float2 T = exp32_entry(bt & 1023);
+  const float q = __fmaf_rn(r, e32::kC3, 0.5f);
+  const float v = __fmul_rn(r, r);
+  const float p = __fmaf_rn(q, v, r);
+  const float s = __fmaf_rn(T.x, p, T.y);
+  n = bt - 0x4B400000;
+  return __fadd_rn(T.x, s);
+}
+// |x| <= 87 (or 0 < x <= 88.7228): the result is a normal binary32
+__device__ __forceinline__ float spec32_exp_core(float x) {
+  int n;
+  const float y = spec32_exp_mant(x, n);
+  return __int_as_float((int)(((unsigned)n >> 10) * 0x00800000u + (unsigned)__float_as_int(y)));   // SHF + LEA
+}
+__device__ __forceinline__ float spec32_expf(float x) {
+  if (fabsf(x) <= 87.0f) return spec32_exp_core(x);
+  if (x != x) return x;
+  if (x > 88.72283172607421875f) return CUDART_INF_F;       // largest binary32 whose exp is finite
+  if (x > 0.0f) return spec32_exp_core(x);                   // 2^127 y still fits
+  if (x < -104.0f) return 0.0f;                              // exp(x) < 2^-150
+  int n;                                                      // subnormal results: one rounding, in the last product
+  const float y = spec32_exp_mant(x, n);
+  const float big = __int_as_float(__float_as_int(y) + (((n >> 10) + 64) << 23));
+  return __fmul_rn(big, 0x1p-64f);
+}
+// exp(x) for |x| <= 2^-6 (the theta update's argument): 1 + x is split exactly into h + e, the Taylor
+// tail x^2 (1/2 + x/6 + x^2/24 + x^3/120) joins e, one final rounding.  != correctly rounded in 1.2e-5 of calls.
+__device__ __forceinline__ float spec32_exp_tiny(float x) {
+  const float h = __fadd_rn(1.0f, x);
+  const float e = __fsub_rn(x, __fsub_rn(h, 1.0f));
+  const float v = __fmul_rn(x, x);
+  float u = __fmaf_rn(x, 0x1.111112p-7f, 0x1.555556p-5f);   // 1/120, 1/24
+  u = __fmaf_rn(u, x, e32::kC3);
+  u = __fmaf_rn(u, x, 0.5f);
+  return __fadd_rn(h, __fmaf_rn(v, u, e));
+}
+__device__ __forceinline__ float spec32_expf_small(float x) {
+  if (fabsf(x) <= 0.015625f) return spec32_exp_tiny(x);
+  return spec32_expf(x);
+}
+
 __device__ __forceinline__ float spec_logf(float x) {
   if (!(x > 0.0f)) return (x == 0.0f) ? -CUDART_INF_F : CUDART_NAN_F;
   if (x == CUDART_INF_F) return x;
