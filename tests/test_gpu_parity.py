@@ -135,6 +135,83 @@ def test_c2_shape_pressure_levels_bitexact(core, oracle_mod, source, ml_depth, s
         assert (np.asarray(got[2]) != libm[2]).mean() < 1e-3
 
 
+@pytest.mark.parametrize('source', SOURCES)
+@pytest.mark.parametrize('adiabat', ADIABATS)
+def test_pressure_levels_every_source_and_adiabat_bitexact(core, oracle_mod, source, adiabat):
+    """Pressure-level grids for every source x adiabat (with test_c1_* this covers all 24 instantiations of
+    the CAPE kernel), global-mix columns (gated ones included), odd column count."""
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C2', cols=(500_000, 504_001), active=False)
+    args = (d['p'], d['t'], d['td'], d['ps'], d['ts'], d['tds'])
+    kw = dict(source=source, ml_depth=400., adiabat=adiabat, pinc=500., vertical_lev='pressure')
+    got = core.calc_cape(*args, method='cuda', **kw)
+    ref = oracle_mod.calc_cape_ref(*args, tmode=oracle_mod.SPEC, nthreads=8, **kw)
+    assert_bitexact(got, ref, f'C2-shape {source} {adiabat}')
+
+
+@pytest.mark.parametrize('cfg,vertical_lev,ncol', [('C1', 'sigma', 1000), ('C2', 'pressure', 8191), ('C5', 'sigma', 1537)])
+@pytest.mark.parametrize('source', SOURCES)
+def test_two_column_kernel_matches_one_column_kernel(core, cfg, vertical_lev, ncol, source, monkeypatch):
+    """The shipping faithful kernel carries two columns per thread in packed binary32 arithmetic
+    (cape_kernel2.cuh); XCAPE_B200_CAPE_KERNEL=1 selects the one-column kernel.  Same bits, counters included."""
+    from xcape_b200.cape_cuda import cape as cape_cuda
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings(cfg, cols=(0, ncol), active=False, **({'grid': (721, 1440)} if cfg == 'C5' else {}))
+    p1d = d['p'].ndim == 1
+    src = {'surface': 1, 'most-unstable': 2, 'mixed-layer': 3}[source]
+
+    def run(adiabat):
+        p = d['p'] if p1d else d['p'].T
+        return cape_cuda(p, d['t'].T, d['td'].T, d['ps'], d['ts'], d['tds'], 1 if p1d else 0, None, src, 500., adiabat, 500.,
+                         2 if p1d else 1, return_counters=True)
+    for adiabat in (1, 2, 3, 4):
+        monkeypatch.delenv('XCAPE_B200_CAPE_KERNEL', raising=False)
+        two = run(adiabat)
+        monkeypatch.setenv('XCAPE_B200_CAPE_KERNEL', '1')
+        one = run(adiabat)
+        for a, b, name in zip(two, one, ('cape', 'cin', 'mulev', 'zmulev', 'status', 'n_iter')):
+            assert np.array_equal(a, b), f'{cfg} {source} adiabat {adiabat}: {name} differs in {(a != b).sum()} columns'
+
+
+@pytest.mark.parametrize('cfg,source,ml_depth,vertical_lev', [
+    ('C2', 'most-unstable', 500., 'pressure'),      # BASELINE configs[1]: 1 038 240 columns x 37 levels
+    ('C3', 'mixed-layer', 500., 'sigma'),           # configs[2]: 1 905 141 columns x 50 levels
+    ('C5', 'most-unstable', 500., 'sigma')])        # one 721 x 1440 x 137 time step of configs[4]
+def test_full_field_bitexact_against_oracle(core, oracle_mod, cfg, source, ml_depth, vertical_lev):
+    """EVERY column of the BASELINE grids against the oracle in SPEC arithmetic, bit for bit (CAPE, CIN, MU level,
+    zMUlev) — the oracle takes ~10-20 s per field on the GPU box's host cores."""
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings(cfg, winds=False, **({'grid': (721, 1440)} if cfg == 'C5' else {}))
+    args = (d['p'], d['t'], d['td'], d['ps'], d['ts'], d['tds'])
+    kw = dict(source=source, ml_depth=ml_depth, adiabat='pseudo-liquid', pinc=500., vertical_lev=vertical_lev)
+    got = core.calc_cape(*args, method='cuda', **kw)
+    ref = oracle_mod.calc_cape_ref(*args, tmode=oracle_mod.SPEC, nthreads=os.cpu_count() or 8, **kw)
+    assert got[0].size == d['ts'].size
+    assert_bitexact(got, ref, f'full {cfg}')
+
+
+@pytest.mark.parametrize('top_first', [False, True])
+def test_float64_or_integer_1d_arguments_next_to_float32_fields(core, top_first):
+    """float32 ERA5 fields with a float64 / int64 `level` axis and float64 surface pressure: same results as the
+    all-float32 call whenever the start levels agree, and the start levels follow ps - p in the WIDER dtype
+    (core.py:286-289) — a surface pressure a hair below a level must not round up onto it."""
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C2', cols=(0, 5000))
+    p, t, td = d['p'].copy(), d['t'].copy(), d['td'].copy()
+    ps64 = d['ps'].astype(np.float64)
+    ps64[:50] = 975.0 - 1e-9                  # float32(ps) == 975.0 == p[1]: float32 keeps level 2, float64 must not
+    order = 'top_first' if top_first else 'surface_first'
+    if top_first:
+        p, t, td = p[::-1].copy(), t[:, ::-1].copy(), td[:, ::-1].copy()
+    kw = dict(source='most-unstable', pinc=500., vertical_lev='pressure', level_order=order)
+    ref = core.calc_cape(p.astype(np.float64), t.astype(np.float64), td.astype(np.float64), ps64, d['ts'].astype(np.float64),
+                         d['tds'].astype(np.float64), **kw)               # everything float64: the round-1 behaviour
+    for pax in (p.astype(np.float64), np.round(p).astype(np.int64) if np.all(p == np.round(p)) else p.astype(np.float64)):
+        got = core.calc_cape(pax, t, td, ps64, d['ts'], d['tds'], **kw)
+        for g, r in zip(got, ref):
+            assert np.array_equal(g, r)
+
+
 def test_c5_shape_137_levels_bitexact(core, oracle_mod):
     from xcape_b200.synthetic import make_soundings
     d = make_soundings('C5', cols=(0, 6000))

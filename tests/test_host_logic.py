@@ -73,6 +73,26 @@ def test_columns_views_are_zero_copy_and_layouts():
     assert core._grid_shape((9, 4, 6), 0) == (4, 6)
 
 
+def test_float32_fields_with_wider_1d_arguments_stay_float32_and_zero_copy():
+    """a float64 / integer pressure axis or float64 surface values next to float32 3-D fields (the usual
+    ERA5 case) must not drag the fields through a float64 host copy — f2py casts each argument separately."""
+    t = np.random.default_rng(0).normal(size=(37, 1000)).astype(np.float32)      # level-major, dense
+    td = t - 1
+    for p in (np.arange(37.), np.arange(37), np.arange(37, dtype=np.float32)):
+        for ps in (np.zeros(1000), np.zeros(1000, np.float32)):
+            f3, f1, p_, dt, layout, mem, ref = A.prepare_fields([t, td], [ps, ps, ps], p=p, dtype_from='fields')
+            assert dt == _lib.F32 and layout == _lib.LEVEL_MAJOR
+            assert f3[0] is t and f3[1] is td                                   # zero-copy
+            assert all(a.dtype == np.float32 for a in f1) and p_.dtype == np.float32
+    # a float64 3-D field still promotes the group (the C ABI takes one dtype)
+    *_, dt, _, _, _ = A.prepare_fields([t, td.astype(np.float64)], [np.zeros(1000, np.float32)], dtype_from='fields')
+    assert dt == _lib.F64
+    from xcape_b200.cape_cuda import _wider_than_fields
+    assert _wider_than_fields([np.arange(37.), np.zeros(4, np.float32)], [t, td])
+    assert not _wider_than_fields([np.arange(37, dtype=np.float32), np.zeros(4, np.float32)], [t, td])
+    assert not _wider_than_fields([np.arange(37.)], [t.astype(np.float64)])
+
+
 @pytest.mark.parametrize('ncol', [0, 1, 127, 128, 129, 1000, 721 * 1440, 24 * 721 * 1440])
 @pytest.mark.parametrize('n', [1, 2, 3, 4, 8])
 def test_column_blocks_partition(ncol, n):

@@ -109,10 +109,16 @@ def device_of(ref, device):
     return int(device)
 
 
-def prepare_fields(fields3d, fields1d, p=None):
+def prepare_fields(fields3d, fields1d, p=None, dtype_from='all'):
     """Bring a group of (nlev, ncol) fields + (ncol,) surface fields (+ optional 1-D p) to one
     dtype, one dense layout and one memory space.  Returns (f3, f1, p, dtype_code, layout,
-    mem, ref) — copies are only made where f2py would have made them too."""
+    mem, ref) — copies are only made where f2py would have made them too.
+
+    ``dtype_from='fields'``: the common dtype is taken from the 3-D fields alone and the per-column /
+    per-level 1-D arrays are cast to it (``ncol`` resp. ``nlev`` elements) — what f2py does for a
+    single-precision routine, which casts every argument separately.  A float64 ``ps`` or an integer
+    / float64 pressure axis next to float32 fields (the usual ERA5 case: the ``level`` coordinate is
+    int or float64) then no longer drags every 3-D field through a float64 host copy."""
     every = list(fields3d) + list(fields1d) + ([p] if p is not None else [])
     on_dev = [is_cuda(a) for a in every]
     if any(on_dev) and not all(on_dev):
@@ -122,7 +128,7 @@ def prepare_fields(fields3d, fields1d, p=None):
         n3, n1 = len(fields3d), len(fields1d)
         fields3d, fields1d = every[:n3], every[n3:n3 + n1]
         p = every[-1] if p is not None else None
-    dt = common_dtype(every)
+    dt = common_dtype(every[:len(fields3d)] if dtype_from == 'fields' else every)
     fields3d = [cast(a, dt) for a in fields3d]
     fields1d = [dense_1d(cast(a, dt)) for a in fields1d]
     if p is not None:

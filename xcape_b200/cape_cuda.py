@@ -15,6 +15,12 @@ from . import _lib
 from .sharding import column_blocks, run_on_devices
 
 
+def _wider_than_fields(one_d, fields):
+    """True if a 1-D argument is not float32 while every 3-D field is (the mixed-dtype case of ERA5 inputs)."""
+    name = lambda a: str(a.dtype).replace('torch.', '')
+    return all(name(f) == 'float32' for f in fields) and any(name(a) != 'float32' for a in one_d)
+
+
 def cape(p_2d, t_2d, td_2d, p_s, t_s, td_s, flag_1d, pres_lev_pos, source, ml_depth, adiabat, pinc,
          type_grid, *, device=0, devices=None, stream=None, precision='faithful', return_status=False,
          return_counters=False, top_first=False):
@@ -54,15 +60,24 @@ def cape(p_2d, t_2d, td_2d, p_s, t_s, td_s, flag_1d, pres_lev_pos, source, ml_de
     else:
         raise ValueError('type_grid must be 1 (model levels) or 2 (pressure levels)')
 
+    # The reference's routine is single precision and f2py casts each argument to float32 separately
+    # (SURVEY §8b "Ownership"), so the working dtype follows the 3-D fields; 1-D arguments are cast to it.
     if p_is_1d:
-        f3, f1, p, dt, layout, mem, ref = A.prepare_fields([t_2d, td_2d], [p_s, t_s, td_s], p=p_2d)
+        if pres_lev_pos is None and _wider_than_fields([p_2d, p_s], [t_2d, td_2d]):
+            # core.py:286-289 evaluates ps - p in the arrays' own (wider) dtype: keep that for the start levels
+            p_up = p_2d.reshape(-1)
+            if top_first:                         # start levels count from the surface whatever the storage order
+                p_up = p_up.flip(0) if A.is_torch(p_up) else p_up[::-1]
+            pres_lev_pos = _device_pres_lev_pos(p_up, p_s, device=A.device_of(t_2d, devices[0] if devices else device),
+                                                stream=stream)
+        f3, f1, p, dt, layout, mem, ref = A.prepare_fields([t_2d, td_2d], [p_s, t_s, td_s], p=p_2d, dtype_from='fields')
         t_, td_ = f3
         if p.shape[0] != nlev:
             raise ValueError('p must have nlev entries')
     else:
         if tuple(p_2d.shape) != (nlev, ngrid):
             raise ValueError('p_2d must have the shape of t_2d on model levels')
-        f3, f1, _, dt, layout, mem, ref = A.prepare_fields([p_2d, t_2d, td_2d], [p_s, t_s, td_s])
+        f3, f1, _, dt, layout, mem, ref = A.prepare_fields([p_2d, t_2d, td_2d], [p_s, t_s, td_s], dtype_from='fields')
         p, t_, td_ = f3
     ps_, ts_, tds_ = f1
     if tuple(td_.shape) != (nlev, ngrid) or any(a.shape[0] != ngrid for a in f1):
@@ -147,3 +162,6 @@ def pres_lev_pos(p_1d, p_s, *, device=0, stream=None):
                                    A.device_of(ps_, device), A.stream_of(ps_, stream))
     _lib.check(rc)
     return out
+
+
+_device_pres_lev_pos = pres_lev_pos     # cape() has a parameter of the same name

@@ -122,6 +122,11 @@ def _any_dask_array(*args):
     return da is not None and any(isinstance(a, da.Array) for a in args)
 
 
+def _concrete(a):
+    """numpy array of a small argument that may be chunked (the shared 1-D pressure axis)."""
+    return np.asarray(a.compute() if hasattr(a, 'compute') else a)
+
+
 def _cape_dummy(*args, **kwargs):
     """The reference's fake backend for shape tests (core.py:107-121)."""
     p, t, td, ps, ts, tds = args
@@ -179,7 +184,7 @@ def _calc_cape_gufunc(*args, **kwargs):
     dtypes = ('f4', 'f4', 'i4', 'f4')[:n_out]
     if p_is_1d:
         # a 1-D pressure axis is shared by every block: bind it instead of broadcasting it
-        p = np.asarray(args[0])
+        p = _concrete(args[0])
         sig = ','.join(['(i)'] * 2 + ['()'] * 3) + '->' + ','.join(['()'] * n_out)
         return da.apply_gufunc(lambda t, td, ps, ts, tds, **kw: _calc_cape_numpy(p, t, td, ps, ts, tds, **kw),
                                sig, *args[1:], output_dtypes=dtypes, axis=-1, vectorize=False, **kwargs)
@@ -263,7 +268,7 @@ def _calc_srh_gufunc(*args, **kwargs):
     dtypes = ('f8', 'f8') + ('f4',) * 6
     outs = ','.join(['()'] * n_out)
     if args[0].ndim == 1:
-        p = np.asarray(args[0])
+        p = _concrete(args[0])
         sig = ','.join(['(i)'] * 4 + ['()'] * 5) + '->' + outs
         return da.apply_gufunc(lambda t, td, u, v, ps, ts, tds, us, vs, **kw:
                                _calc_srh_numpy(p, t, td, u, v, ps, ts, tds, us, vs, **kw),

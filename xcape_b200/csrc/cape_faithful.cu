@@ -6,6 +6,10 @@
 #include "xc_common.cuh"
 #include "xc_math_spec.cuh"
 #include "cape_kernel.cuh"
+#if !defined(XC_FAST_TU) && !defined(XC_FAST_RELAXED_TU)
+#include "cape_kernel2.cuh"
+#include <cstdlib>
+#endif
 
 namespace xc {
 
@@ -48,6 +52,20 @@ using MathPolicy = MathSpec;
 
 template <int SOURCE, int ADIABAT, bool P1D>
 static int launch(const CapeArgs& a, cudaStream_t s) {
+#if !defined(XC_FAST_TU) && !defined(XC_FAST_RELAXED_TU)
+  // faithful arithmetic: the two-column packed kernel (cape_kernel2.cuh); XCAPE_B200_CAPE_KERNEL=1 selects the
+  // one-column kernel (same results bit for bit; kept for A/B timing)
+  const char* which = getenv("XCAPE_B200_CAPE_KERNEL");      // read per call: tests flip it to cross-check the two kernels
+  if (!(which && which[0] == '1')) {
+    const int threads2 = XC_CAPE2_THREADS;
+    const int64_t pairs = (a.ncol + 1) / 2;
+    const int64_t blocks2 = (pairs + threads2 - 1) / threads2;
+    if (blocks2 <= 0) return XCAPE_OK;
+    cape_kernel2<MathPolicy, SOURCE, ADIABAT, P1D><<<(unsigned)blocks2, threads2, 0, s>>>(a);
+    XC_LAUNCH_CHECK();
+    return XCAPE_OK;
+  }
+#endif
   const int threads = XC_CAPE_THREADS;
   const int64_t blocks = (a.ncol + threads - 1) / threads;
   if (blocks <= 0) return XCAPE_OK;

@@ -1,0 +1,420 @@
+// cape_kernel2.cuh — the FAITHFUL CAPE/CIN kernel for sm_100a: TWO columns per thread, moist iteration in
+// packed binary32 arithmetic (FFMA2 / FADD2 / FMUL2 — instructions that exist from sm_100 on).
+//
+// Why (ncu r2a): with the exp in binary32 the one-column kernel is bound by instruction ISSUE
+// (84 % of the slots busy, 4 eligible warps per scheduler), and 75 % of what it issues are FP32 adds, multiplies
+// and fmas of the moist fixed-point body.  A packed instruction does the same IEEE-rounded operation on two
+// independent values for ONE issue slot (measured: FFMA2 sustains the same flop rate as FFMA with half the
+// instructions, profiles/lab/f2_probe.cu), so a thread that carries the two adjacent columns 2t and 2t+1 through
+// the iteration together needs ~60 issue slots per column-pass instead of ~91, and the bound moves from the
+// issue port to the FMA pipe itself.
+//
+// Every packed operation is the same round-to-nearest binary32 operation the one-column kernel (and the
+// reference) performs, applied lane-wise, so results are bit-identical to cape_kernel.cuh — the parity tests do
+// not know which kernel ran.  Everything that is not the moist iteration (source parcel, per-level environment,
+// sub-step prologue, buoyancy integration, the general fall-back loop) is the scalar code of cape_kernel.cuh
+// run once per column.
+//
+// Structure of the ascent (differences from the one-column kernel, none of which changes a result):
+//  * layers are walked by ABSOLUTE level index, so lanes (and the two columns of a thread) whose parcels start
+//    at different levels meet the same layer — and therefore the same number of sub-steps on pressure grids —
+//    in the same loop trip (profiles/divergence_model.py: 2501 -> 2398 loop trips per warp);
+//  * the pressure window that licenses the unguarded log / pow / division of the sub-step prologue and the
+//    temperature bound tmax of the moist window are evaluated once per LAYER, at the layer's top pressure,
+//    instead of once per sub-step.
+#pragma once
+#include "cape_kernel.cuh"
+
+namespace xc {
+
+using f2 = float2;
+__device__ __forceinline__ f2 splat(float x) { return make_float2(x, x); }
+__device__ __forceinline__ f2 vneg(f2 a) { return make_float2(-a.x, -a.y); }            // folds into an operand modifier
+__device__ __forceinline__ f2 vadd(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 vsub(f2 a, f2 b) { return __fadd2_rn(a, vneg(b)); }
+__device__ __forceinline__ f2 vmul(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 vfma(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+// ptxas 12.9 contracts a packed multiply whose only use is a packed add into FFMA2 even under --fmad=false and with
+// explicit .rn on both PTX instructions (it does not for the scalar forms).  Where the reference rounds the
+// product first (a*b + c written as two operations), the add is therefore done as two scalar FADDs, which ptxas
+// leaves alone; tests/test_gpu_parity.py's bit-exact comparisons would expose any contraction that slipped in.
+__device__ __forceinline__ f2 sadd(f2 a, f2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ f2 sadd(f2 a, float b) { return make_float2(__fadd_rn(a.x, b), __fadd_rn(a.y, b)); }
+__device__ __forceinline__ f2 ssub(f2 a, f2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+__device__ __forceinline__ f2 vadd(f2 a, float b) { return __fadd2_rn(a, splat(b)); }
+__device__ __forceinline__ f2 vmul(f2 a, float b) { return __fmul2_rn(a, splat(b)); }
+__device__ __forceinline__ f2 vfma(f2 a, float b, float c) { return __ffma2_rn(a, splat(b), splat(c)); }
+__device__ __forceinline__ f2 vfma(f2 a, f2 b, float c) { return __ffma2_rn(a, b, splat(c)); }
+__device__ __forceinline__ f2 vfma(f2 a, float b, f2 c) { return __ffma2_rn(a, splat(b), c); }
+
+// fdiv_fast (cape_kernel.cuh) on both halves: two MUFU.RCP, five packed fmas
+__device__ __forceinline__ f2 vdiv_fast(f2 a, f2 b) {
+  f2 r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(b.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(b.y));
+  const f2 e = vfma(vneg(b), r, 1.0f);
+  r = vfma(r, e, r);
+  const f2 q = vfma(a, r, 0.0f);
+  const f2 rem = vfma(vneg(b), q, a);
+  return vfma(r, rem, q);
+}
+
+// spec32_exp_core (xc_math_spec.cuh) on both halves; |x| <= 87
+__device__ __forceinline__ f2 vexp32_core(f2 x) {
+  const f2 t = vfma(x, e32::kKL, e32::kMagic);
+  const f2 nf = vadd(t, -e32::kMagic);
+  f2 r = vfma(nf, -e32::kL1, x);
+  r = vfma(nf, -e32::kL2, r);
+  const int bx = __float_as_int(t.x), by = __float_as_int(t.y);
+  const int jx = bx & 1023, jy = by & 1023;
+  const f2 Th = make_float2(exp32_hi(jx), exp32_hi(jy)), Tl = make_float2(exp32_lo(jx), exp32_lo(jy));
+  const f2 q = vfma(r, e32::kC3, 0.5f);
+  const f2 v = vmul(r, r);
+  const f2 p = vfma(q, v, r);
+  const f2 y = vadd(Th, vfma(Th, p, Tl));
+  f2 o;
+  o.x = __int_as_float((int)(((unsigned)(bx - 0x4B400000) >> 10) * 0x00800000u + (unsigned)__float_as_int(y.x)));
+  o.y = __int_as_float((int)(((unsigned)(by - 0x4B400000) >> 10) * 0x00800000u + (unsigned)__float_as_int(y.y)));
+  return o;
+}
+// spec32_exp_tiny on both halves; |x| <= 2^-6
+__device__ __forceinline__ f2 vexp32_tiny(f2 x) {
+  const f2 h = vadd(x, 1.0f);
+  const f2 e = vsub(x, vadd(h, -1.0f));
+  const f2 v = vmul(x, x);
+  f2 u = vfma(x, 0x1.111112p-7f, 0x1.555556p-5f);
+  u = vfma(u, x, e32::kC3);
+  u = vfma(u, x, 0.5f);
+  return vadd(h, vfma(v, u, e));
+}
+__device__ __forceinline__ f2 vqsat(f2 p, f2 t, float a, float b) {   // getqvs / getqvi inside the window (f90:570-598)
+  const f2 x = vdiv_fast(vmul(vadd(t, -273.15f), a), vadd(t, -b));
+  const f2 es = vmul(vexp32_core(x), 611.2f);
+  return vdiv_fast(vmul(es, cc::eps_q), ssub(p, es));
+}
+
+// moist_arg<M, ICE, true> of cape_kernel.cuh on both halves (same operations in the same order)
+template <bool ICE, bool PSEUDO>
+__device__ __forceinline__ f2 vmoist_arg(f2 t2, f2 p2, f2 qt, f2 t1, f2 qv1, f2 ql1, f2 qi1, f2 logp, f2& qv2, f2& ql2, f2& qi2) {
+  f2 fice;
+  if (ICE) {
+    f2 fl = vdiv_fast(vadd(t2, -233.15f), splat(273.15f - 233.15f));
+    fl.x = fmaxf(fminf(fl.x, 1.0f), 0.0f);
+    fl.y = fmaxf(fminf(fl.y, 1.0f), 0.0f);
+    fice = vsub(splat(1.0f), fl);
+    const f2 qs = sadd(vmul(fl, vqsat(p2, t2, 17.67f, 29.65f)), vmul(fice, vqsat(p2, t2, 21.8745584f, 7.66f)));
+    qv2 = make_float2(fminf(qt.x, qs.x), fminf(qt.y, qs.y));
+    f2 w = vmul(fice, vsub(qt, qv2));
+    qi2 = make_float2(fmaxf(w.x, 0.0f), fmaxf(w.y, 0.0f));
+    w = vsub(vsub(qt, qv2), qi2);
+    ql2 = make_float2(fmaxf(w.x, 0.0f), fmaxf(w.y, 0.0f));
+  } else {
+    const f2 qs = vqsat(p2, t2, 17.67f, 29.65f);
+    qv2 = make_float2(fminf(qt.x, qs.x), fminf(qt.y, qs.y));
+    qi2 = splat(0.0f);
+    const f2 w = vsub(qt, qv2);
+    ql2 = make_float2(fmaxf(w.x, 0.0f), fmaxf(w.y, 0.0f));
+  }
+  const f2 tbar = vmul(vadd(t1, t2), 0.5f);
+  const f2 qvbar = vmul(vadd(qv1, qv2), 0.5f);
+  const f2 qlbar = PSEUDO ? vmul(ql2, 0.5f) : vmul(vadd(ql1, ql2), 0.5f);       // ql1 = 0: 0 + x = x
+  const f2 lhv = sadd(vmul(tbar, -cc::lv2), cc::lv1);                          // lv1 - lv2*tbar
+  const f2 rm = sadd(vmul(qvbar, cc::rv), cc::rd);
+  f2 cpm = sadd(sadd(vmul(qvbar, cc::cpv), cc::cp), vmul(qlbar, cc::cpl));
+  const f2 dql = PSEUDO ? ql2 : vsub(ql2, ql1);
+  f2 arg;
+  if (ICE) {
+    const f2 qibar = PSEUDO ? vmul(qi2, 0.5f) : vmul(vadd(qi1, qi2), 0.5f);
+    const f2 lhs = sadd(vmul(tbar, -cc::ls2), cc::ls1);
+    cpm = sadd(cpm, vmul(qibar, cc::cpi));
+    const f2 den = vmul(cpm, tbar);
+    const f2 dqi = PSEUDO ? qi2 : vsub(qi2, qi1);
+    arg = vadd(vdiv_fast(vmul(lhv, dql), den), vdiv_fast(vmul(lhs, dqi), den));
+  } else {
+    arg = vdiv_fast(vmul(lhv, dql), vmul(cpm, tbar));
+  }
+  return sadd(arg, vmul(vadd(vdiv_fast(rm, cpm), -cc::rddcp), logp));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-column state of the ascent
+struct Col2 {
+  int64_t c;            // column index
+  int ks, nk;           // first 3-D level used (1-based), levels of the assembled column
+  int k;                // assembled index of the level the parcel is at
+  int lev_next;         // absolute 0-based index of the 3-D level that tops the next layer
+  bool live;            // the column has a result to write
+  bool active;          // still ascending
+  int st, iters, mulvl;
+  float zout, cape, cin, narea, z, b2;
+  float th2, pi2, p2, t2, qv2, ql2, qi2, qt;
+  float prev_p, prev_pi, prev_thv;
+};
+struct Layer2 {         // what a column knows about the layer it is crossing
+  bool in;              // the column takes part in this layer
+  bool fastp;           // every pressure of the layer lies in [2, 5e6] Pa: unguarded log / pow / division in the prologue
+  float tmax;           // upper end of the moist window's temperature range for this layer (< 0: no window)
+  float dp, b1;
+  int nloop;
+  float cur_p, cur_pi, cur_thv;
+};
+struct Sub2 {           // start state of a sub-step
+  float p1, t1, th1, qv1, ql1, qi1, logp;
+  bool window;
+};
+
+template <class M, int SOURCE, bool P1D>
+__device__ __forceinline__ void col2_init(const CapeArgs& a, int64_t c, Col2& C) {
+  C.c = c; C.live = (c < a.ncol); C.active = false;
+  C.st = 0; C.iters = 0; C.mulvl = 0; C.zout = 0.0f; C.cape = 0.0f; C.cin = 0.0f; C.narea = 0.0f; C.z = 0.0f; C.b2 = 0.0f;
+  C.th2 = C.pi2 = C.p2 = C.t2 = C.qv2 = C.ql2 = C.qi2 = C.qt = 0.0f;
+  C.prev_p = C.prev_pi = C.prev_thv = 0.0f; C.ks = 1; C.nk = 1; C.k = 1; C.lev_next = 0;
+  if (!C.live) return;
+  if (!(a.ts[c] > 0.0f)) { C.st = 1; return; }      // model_lev.f90:77,83-88 (degC gate): zeros, MUlvl 0
+  int ks = a.start ? a.start[c] : 1;                // pressure_lev.f90:154-160
+  ks = ks < 1 ? 1 : (ks > a.nlev ? a.nlev : ks);
+  C.ks = ks; C.nk = a.nlev - ks + 2;
+  const Parcel P = select_source<M, SOURCE, P1D>(a, c, ks, C.nk);
+  C.k = P.k; C.z = P.zk; C.mulvl = P.mulvl; C.zout = -999999.0f;
+  C.th2 = P.th2; C.pi2 = P.pi2; C.p2 = P.p2; C.t2 = P.t2; C.qv2 = P.qv2; C.b2 = P.b2; C.qt = P.qv2;
+  C.prev_p = P.prev.p; C.prev_pi = P.prev.pi; C.prev_thv = P.prev.thv;
+  C.lev_next = ks + C.k - 2;
+  C.active = C.k < C.nk;
+}
+
+// f90:403-415 — the layer's environment, sub-step count, and the per-layer windows
+template <class M, bool P1D, bool ICE>
+__device__ __forceinline__ void col2_layer_begin(const CapeArgs& a, Col2& C, Layer2& Y) {
+  C.k = C.k + 1;
+  const Env cur = load_env<M, P1D>(a, C.c, C.ks, C.k);
+  Y.cur_p = cur.p; Y.cur_pi = cur.pi; Y.cur_thv = cur.thv;
+  Y.b1 = C.b2;
+  float dp = C.prev_p - cur.p;
+  int nloop = 1;
+  if (!(dp < a.pinc)) {
+    const float r = dp / a.pinc;
+    if (!(r < (float)cc::nloop_cap)) { C.st = 3; C.active = false; Y.in = false; return; }   // see cape_kernel.cuh
+    nloop = 1 + (int)r;
+    dp = dp / (float)nloop;
+  }
+  Y.dp = dp; Y.nloop = nloop;
+  // p2 starts within a few ulps of prev_p and ends within a few ulps of cur_p
+  const float plo = fminf(C.prev_p, cur.p), phi = fmaxf(C.prev_p, cur.p);
+  Y.fastp = (plo >= 2.0f) && (phi <= 5e6f) && (C.p2 >= 2.0f) && (C.p2 <= 5e6f);
+  Y.tmax = -1.0f;
+  if (Y.fastp) {
+    // es(T) = 0.3 p inverted with approximate math at (just below) the layer's lowest pressure: tmax only chooses
+    // between two code paths with identical results, and a smaller p gives a smaller (safer) tmax
+    const float lg = __logf((0.999f * plo) * (0.3f / 611.2f));
+    Y.tmax = fminf(__fdividef(4826.5605f - 29.65f * lg, 17.67f - lg), 400.0f);
+  }
+}
+
+// sub-step prologue (f90:417-434): shift the state, step the pressure, Exner function and ln(p2/p1)
+template <class M, bool PSEUDO>
+__device__ __forceinline__ void col2_sub_begin(Col2& C, const Layer2& Y, Sub2& S) {
+  S.p1 = C.p2; S.t1 = C.t2; S.th1 = C.th2; S.qv1 = C.qv2;
+  S.ql1 = PSEUDO ? 0.0f : C.ql2;                   // pseudo-adiabats reset condensate each sub-step (f90:487-491)
+  S.qi1 = PSEUDO ? 0.0f : C.qi2;
+  C.p2 = C.p2 - Y.dp;
+  if (Y.fastp && C.p2 >= 2.0f) {
+    // all operands normal and far from the range ends: the unguarded cores give what M::pow / M::log / `/` give
+    C.pi2 = __double2float_rn(spec_exp_core(__dmul_rn((double)cc::rddcp, spec_log_core((double)(C.p2 * cc::rp00)))));
+    S.logp = __double2float_rn(spec_log_core((double)fdiv_fast(C.p2, S.p1)));
+    S.window = (Y.tmax >= 100.0f) && (S.t1 >= 90.0f) && (S.t1 <= 400.0f) && (C.qt >= 0.0f) && (C.qt <= 1.0f) &&
+               (S.ql1 <= 1.0f) && (S.qi1 <= 1.0f) && (fabsf(S.th1) < CUDART_INF_F);
+  } else {
+    C.pi2 = M::pow(C.p2 * cc::rp00, cc::rddcp);
+    S.logp = M::log(C.p2 / S.p1);
+    S.window = false;
+  }
+}
+
+// the reference's loop verbatim (slow divisions, guarded exp): columns outside the windows.  Everything by value:
+// a reference parameter of a non-inlined function would pin the caller's column state to local memory.
+struct SubOut { float t2, th2, qv2, ql2, qi2; int i, st; };
+template <class M, bool ICE>
+__device__ __noinline__ SubOut col2_sub_general(float pi2, float p2, float qt, float t1, float th1, float qv1, float ql1, float qi1,
+                                                float logp, int st) {
+  SubOut o;
+  o.st = st;
+  int i = 0;
+  float thlast = th1;
+  for (;;) {
+    i = i + 1;
+    o.t2 = thlast * pi2;
+    o.th2 = moist_body<M, ICE, false>(o.t2, p2, qt, t1, th1, qv1, ql1, qi1, logp, o.qv2, o.ql2, o.qi2);
+    if (i > 100) { o.st = 2; break; }             // f90:464-474 lack of convergence
+    if (fabsf(o.th2 - thlast) > cc::converge) thlast = thlast + 0.3f * (o.th2 - thlast);
+    else break;
+  }
+  o.i = i;
+  return o;
+}
+
+template <bool PSEUDO>
+__device__ __forceinline__ void col2_sub_end(Col2& C, int i) {
+  C.iters += i;
+  if (C.iters > cc::iter_budget) C.st = 3;
+  if (C.st) { C.active = false; return; }
+  if (PSEUDO) { C.qt = C.qv2; C.ql2 = 0.0f; C.qi2 = 0.0f; }
+}
+
+// f90:501-558 — buoyancy, trapezoid CAPE / CIN with zero-crossing split, stop rule
+__device__ __forceinline__ void col2_layer_end(Col2& C, const Layer2& Y) {
+  const float thv2 = C.th2 * (1.0f + cc::reps * C.qv2) / (1.0f + C.qv2 + C.ql2 + C.qi2);
+  const float b1 = Y.b1;
+  const float b2 = cc::g * (thv2 - Y.cur_thv) / Y.cur_thv;
+  const float dz = -cc::cpdg * 0.5f * (Y.cur_thv + C.prev_thv) * (Y.cur_pi - C.prev_pi);
+  float parea;
+  if (b2 >= 0.0f && b1 < 0.0f) {
+    const float frac = b2 / (b2 - b1);
+    parea = 0.5f * b2 * dz * frac;
+    C.narea = C.narea - 0.5f * b1 * dz * (1.0f - frac);
+    C.cin = C.cin + C.narea;
+    C.narea = 0.0f;
+  } else if (b2 < 0.0f && b1 > 0.0f) {
+    const float frac = b1 / (b1 - b2);
+    parea = 0.5f * b1 * dz * frac;
+    C.narea = -0.5f * b2 * dz * (1.0f - frac);
+  } else if (b2 < 0.0f) {
+    parea = 0.0f;
+    C.narea = C.narea - 0.5f * dz * (b1 + b2);
+  } else {
+    parea = 0.5f * dz * (b1 + b2);
+    C.narea = 0.0f;
+  }
+  C.cape = C.cape + fmax_(0.0f, parea);
+  C.b2 = b2;
+  C.z = C.z + dz;
+  C.zout = C.z;
+  C.prev_p = Y.cur_p; C.prev_pi = Y.cur_pi; C.prev_thv = Y.cur_thv;
+  C.lev_next = C.lev_next + 1;
+  if ((Y.cur_p <= 10000.0f && b2 < 0.0f) || !(C.k < C.nk)) C.active = false;
+}
+
+__device__ __forceinline__ void col2_store(const CapeArgs& a, const Col2& C) {
+  if (!C.live) return;
+  const bool failed = C.st >= 2;
+  a.cape[C.c] = failed ? 0.0f : C.cape;
+  a.cin[C.c] = failed ? 0.0f : C.cin;
+  a.zout[C.c] = C.zout;
+  a.mulvl[C.c] = C.mulvl;
+  if (a.status) a.status[C.c] = C.st;
+  if (a.n_iter) a.n_iter[C.c] = C.iters;
+}
+
+#ifndef XC_CAPE2_THREADS
+#define XC_CAPE2_THREADS 128
+#endif
+#ifndef XC_CAPE2_MIN_BLOCKS
+#define XC_CAPE2_MIN_BLOCKS 5    // <= 102 registers.  Measured per ERA5 field (ms): 4 CTAs 8.88, 5 CTAs 8.66, 6 CTAs 8.71, 3 x 256 threads 8.63:
+#endif                           // the kernel is bound by FMA-pipe / register-file bandwidth, not by occupancy
+template <class M, int SOURCE, int ADIABAT, bool P1D>
+__global__ void __launch_bounds__(XC_CAPE2_THREADS, XC_CAPE2_MIN_BLOCKS) cape_kernel2(const CapeArgs a) {
+  exp32_smem_fill();
+  constexpr bool ICE = (ADIABAT == 3 || ADIABAT == 4);
+  constexpr bool PSEUDO = (ADIABAT == 1 || ADIABAT == 3);
+  const int64_t c0 = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+  if (c0 >= a.ncol) return;
+
+  Col2 A, B;
+  col2_init<M, SOURCE, P1D>(a, c0, A);
+  col2_init<M, SOURCE, P1D>(a, c0 + 1, B);
+
+  for (int L = 0; L < a.nlev; ++L) {
+    if (!(A.active || B.active)) break;
+    Layer2 YA, YB;
+    YA.in = A.active && A.lev_next == L;
+    YB.in = B.active && B.lev_next == L;
+    if (!(YA.in || YB.in)) continue;
+    YA.nloop = 0; YB.nloop = 0;
+    if (YA.in) col2_layer_begin<M, P1D, ICE>(a, A, YA);
+    if (YB.in) col2_layer_begin<M, P1D, ICE>(a, B, YB);
+    const int nmax = max(YA.in ? YA.nloop : 0, YB.in ? YB.nloop : 0);
+
+    for (int n = 1; n <= nmax; ++n) {
+      const bool doA = YA.in && A.active && n <= YA.nloop;
+      const bool doB = YB.in && B.active && n <= YB.nloop;
+      if (!(doA || doB)) break;
+      Sub2 SA, SB;
+      SA.window = false; SB.window = false;
+      if (doA) col2_sub_begin<M, PSEUDO>(A, YA, SA);
+      if (doB) col2_sub_begin<M, PSEUDO>(B, YB, SB);
+      bool genA = doA, genB = doB;
+      int iA = 0, iB = 0;
+
+      if (SA.window || SB.window) {
+        // ---- window loop, both columns in packed arithmetic.  A column that does not take part rides along
+        // as a copy of the other one (identical arithmetic, so it neither delays convergence nor matters).
+        const bool wa = SA.window, wb = SB.window;
+        const f2 pi2 = make_float2(wa ? A.pi2 : B.pi2, wb ? B.pi2 : A.pi2);
+        const f2 p2 = make_float2(wa ? A.p2 : B.p2, wb ? B.p2 : A.p2);
+        const f2 qt = make_float2(wa ? A.qt : B.qt, wb ? B.qt : A.qt);
+        const f2 t1 = make_float2(wa ? SA.t1 : SB.t1, wb ? SB.t1 : SA.t1);
+        const f2 th1 = make_float2(wa ? SA.th1 : SB.th1, wb ? SB.th1 : SA.th1);
+        const f2 qv1 = make_float2(wa ? SA.qv1 : SB.qv1, wb ? SB.qv1 : SA.qv1);
+        const f2 ql1 = make_float2(wa ? SA.ql1 : SB.ql1, wb ? SB.ql1 : SA.ql1);
+        const f2 qi1 = make_float2(wa ? SA.qi1 : SB.qi1, wb ? SB.qi1 : SA.qi1);
+        const f2 logp = make_float2(wa ? SA.logp : SB.logp, wb ? SB.logp : SA.logp);
+        const f2 tmx = make_float2(wa ? YA.tmax : YB.tmax, wb ? YB.tmax : YA.tmax);
+        const f2 tc = vmul(vadd(tmx, 90.0f), 0.5f);
+        const f2 hw = vmul(vmul(vadd(tmx, -90.0f), 0.5f), 0.999f);   // shrunk: tc +- hw lies inside [90, tmax] for any rounding
+        f2 thlast = th1;
+        f2 dev_t = splat(0.0f), dev_a = splat(0.0f);
+        f2 t2, th2, qv2, ql2, qi2;
+        int lx = 101, ly = 101;                     // `left` at the last pass that ended with the half still moving
+        int left = 100;
+        bool mx, my;
+        do {
+          t2 = vmul(thlast, pi2);
+          const f2 dt = ssub(t2, tc);
+          dev_t.x = fmaxf(dev_t.x, fabsf(dt.x)); dev_t.y = fmaxf(dev_t.y, fabsf(dt.y));
+          const f2 arg = vmoist_arg<ICE, PSEUDO>(t2, p2, qt, t1, qv1, ql1, qi1, logp, qv2, ql2, qi2);
+          dev_a.x = fmaxf(dev_a.x, fabsf(arg.x)); dev_a.y = fmaxf(dev_a.y, fabsf(arg.y));
+          th2 = vmul(th1, vexp32_tiny(arg));
+          const f2 d = ssub(th2, thlast);
+          const f2 step = vmul(d, 0.3f);
+          mx = fabsf(d.x) > cc::converge; my = fabsf(d.y) > cc::converge;
+          // a half that has converged keeps its thlast: the following passes recompute its final pass unchanged
+          if (mx) { thlast.x = thlast.x + step.x; lx = left; }
+          if (my) { thlast.y = thlast.y + step.y; ly = left; }
+          left = left - 1;
+        } while ((mx || my) && left != 0);
+        // pass k runs with left = 101 - k: the half took (101 - l) + 1 passes, or was still moving at pass 100 (l == 1)
+        if (wa) {
+          genA = !(dev_t.x <= hw.x) || !(dev_a.x <= 0.015625f);
+          if (!genA) {
+            A.t2 = t2.x; A.th2 = th2.x; A.qv2 = qv2.x; A.ql2 = ql2.x; A.qi2 = qi2.x;
+            iA = 102 - lx;
+            if (lx == 1) { iA = 101; A.st = 2; }    // the reference runs pass 101 and gives up there (f90:464-474)
+          }
+        }
+        if (wb) {
+          genB = !(dev_t.y <= hw.y) || !(dev_a.y <= 0.015625f);
+          if (!genB) {
+            B.t2 = t2.y; B.th2 = th2.y; B.qv2 = qv2.y; B.ql2 = ql2.y; B.qi2 = qi2.y;
+            iB = 102 - ly;
+            if (ly == 1) { iB = 101; B.st = 2; }
+          }
+        }
+      }
+      if (genA) {
+        const SubOut o = col2_sub_general<M, ICE>(A.pi2, A.p2, A.qt, SA.t1, SA.th1, SA.qv1, SA.ql1, SA.qi1, SA.logp, A.st);
+        A.t2 = o.t2; A.th2 = o.th2; A.qv2 = o.qv2; A.ql2 = o.ql2; A.qi2 = o.qi2; A.st = o.st; iA = o.i;
+      }
+      if (genB) {
+        const SubOut o = col2_sub_general<M, ICE>(B.pi2, B.p2, B.qt, SB.t1, SB.th1, SB.qv1, SB.ql1, SB.qi1, SB.logp, B.st);
+        B.t2 = o.t2; B.th2 = o.th2; B.qv2 = o.qv2; B.ql2 = o.ql2; B.qi2 = o.qi2; B.st = o.st; iB = o.i;
+      }
+      if (doA) col2_sub_end<PSEUDO>(A, iA);
+      if (doB) col2_sub_end<PSEUDO>(B, iB);
+    }
+    if (YA.in && A.st == 0) col2_layer_end(A, YA);
+    if (YB.in && B.st == 0) col2_layer_end(B, YB);
+  }
+  col2_store(a, A);
+  col2_store(a, B);
+}
+
+}  // namespace xc

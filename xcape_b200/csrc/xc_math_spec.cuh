@@ -338,16 +338,25 @@ constexpr float kC3 = 0x1.555556p-3f;      // RN32(1/6)
 // LDS with a scaled index costs two instructions where the global-memory path costs five (64-bit address
 // arithmetic) plus an L1 round trip.  A kernel that uses the exp32 functions calls exp32_smem_fill() first.
 #ifndef XC_EXP32_GLOBAL_TABLE
-__shared__ float2 sExp32T[1024];
+__shared__ float sExp32Hi[1024];
+__shared__ float sExp32Lo[1024];
 __device__ __forceinline__ void exp32_smem_fill() {
-  for (int k = threadIdx.x; k < 1024; k += blockDim.x) sExp32T[k] = kExp32T[k];
+  for (int k = threadIdx.x; k < 1024; k += blockDim.x) {
+    const float2 T = kExp32T[k];
+    sExp32Hi[k] = T.x; sExp32Lo[k] = T.y;
+  }
   __syncthreads();
 }
-__device__ __forceinline__ float2 exp32_entry(int j) { return sExp32T[j]; }
+// hi and lo parts live in separate arrays so that the two-column kernel can load the four values of a pair
+// straight into the halves of two packed registers
+__device__ __forceinline__ float exp32_hi(int j) { return sExp32Hi[j]; }
+__device__ __forceinline__ float exp32_lo(int j) { return sExp32Lo[j]; }
 #else
 __device__ __forceinline__ void exp32_smem_fill() {}
-__device__ __forceinline__ float2 exp32_entry(int j) { return __ldg(&kExp32T[j]); }
+__device__ __forceinline__ float exp32_hi(int j) { return __ldg(&kExp32T[j].x); }
+__device__ __forceinline__ float exp32_lo(int j) { return __ldg(&kExp32T[j].y); }
 #endif
+__device__ __forceinline__ float2 exp32_entry(int j) { return make_float2(exp32_hi(j), exp32_lo(j)); }
 
 // y in [1, 2) and the integer n (n div 1024 = binary exponent) for |x| <= 104
 __device__ __forceinline__ float spec32_exp_mant(float x, int& n) {
