@@ -18,15 +18,24 @@ Numbers on the JSON line:
   value      whole-job columns/s with the field resident in HBM in the reference's own layout
              ([ncol, nlev] float32, level last); the timed call is the public device-pointer
              path (pres_lev_pos + relayout + kernel), CUDA events on the launch stream.
-  e2e        same metric through the host-buffer C-ABI call (pinned host numpy in, host numpy
-             out, H2D / D2H inside the timed region).
+  e2e        same metric through the PUBLIC call a user makes, core.calc_cape / core.calc_srh(method='cuda'),
+             on pinned host numpy arrays in the reference's layout ([ncol, nlev], level last): host numpy in,
+             host numpy out, H2D / D2H inside the timed region.  Sub-records: `pageable` (ordinary numpy
+             arrays), `level_major_pinned` ([nlev, ncol] = the on-disk order of ERA5 / HRRR files, lev_axis=0:
+             zero relayout, and on pressure grids only the levels the ascent can reach are copied).
   roofline   the dominant kernel alone (level-major input, exactly one launch per step, CUDA
              events).  CAPE: FP-issue bound — algorithmic work = 73 flop x (moist iterations
              executed, counted by the kernel; tests assert the count equals the oracle's) against
              the FFMA peak measured on this GPU by xcape_cuda_measure_peaks, plus the HBM view.
              SRH: HBM bound — 1028 B/column against MEASURED_PEAKS.json's copy bandwidth.
   cpu_baseline  the CPU oracle (= the reference algorithm; CAPE with the libm gfortran links) on
-             all host threads over a bounded sample of the same field (rank 0, N = 1).
+             all host threads AND on one thread over bounded samples of the same field, 3 repeats each,
+             best and median (rank 0, N = 1).
+  kernel_variants  the same kernel on the column-shuffled field (warp-divergence worst case) and on the
+             global-mix field (~45 % of columns gated by ts <= 0 degC).
+  workloads  (N = 1) C3 / C4 / C5 sub-records: kernel ms, device-path ms, columns/s, roofline fraction.
+  strong_scaling_C5  BASELINE configs[4]: the 24-step 721x1440x137 stack, 24/N steps per rank, whole-job
+             columns/s device-resident and end to end (each rank re-uses one synthetic step's buffers).
 """
 import argparse
 import gc
@@ -45,6 +54,7 @@ import numpy as np  # noqa: E402
 
 UNIT = 'columns/s'
 FLOP_PER_ITER = 73.0
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 148 SMs x 128 FP32 lanes x 2 flop/FMA x 1.965 GHz = 74.4
 
 
 class ClockSampler:
@@ -176,9 +186,36 @@ class CapeWorkload:
             hp['p'] = d['p']
         return hp
 
-    def step_e2e(self, hp, device):
-        p = hp['p'] if self.p1d else hp['p'].T
-        return self._call(p, hp['t'].T, hp['td'].T, hp['ps'], hp['ts'], hp['tds'], None, device=device)
+    def step_e2e(self, hp, device, lev_axis=-1):
+        """The public API on host arrays ([ncol, nlev], or [nlev, ncol] with lev_axis=0)."""
+        from xcape_b200 import core
+        return core.calc_cape(hp['p'], hp['t'], hp['td'], hp['ps'], hp['ts'], hp['tds'], source=self.source,
+                              ml_depth=self.ml_depth, adiabat='pseudo-liquid', pinc=500., method='cuda',
+                              vertical_lev='pressure' if self.p1d else 'sigma', device=device, precision=self.precision,
+                              lev_axis=lev_axis)
+
+    def level_major(self, hp, pin=True):
+        """[nlev, ncol] copies of the 3-D host fields (pinned): the on-disk order of ERA5 / HRRR."""
+        import torch
+        out = dict(hp)
+        keep = []
+        for k in self.fields3:
+            a = torch.empty((self.nlev, self.ncol), dtype=torch.float32)
+            a = a.pin_memory() if pin else a
+            a.numpy()[...] = hp[k].T
+            keep.append(a)
+            out[k] = a.numpy()
+        out['_keep_lm'] = keep
+        return out
+
+    def shipped_levels(self):
+        """Levels the host path copies for level-major / pageable input on a pressure grid (api.cu)."""
+        if not self.p1d:
+            return self.nlev
+        from xcape_b200.synthetic import ERA5_LEVELS_HPA
+        below = np.flatnonzero(ERA5_LEVELS_HPA[:self.nlev] <= 100.0)
+        need = int(below[0]) + 1 if below.size else self.nlev
+        return need if need + 2 <= self.nlev else self.nlev
 
     def io_bytes(self):
         h2d = int(len(self.fields3) * self.ncol * self.nlev * 4 + 3 * self.ncol * 4 + (self.nlev * 4 if self.p1d else 0))
@@ -204,9 +241,11 @@ class CapeWorkload:
         traffic, traffic_src = ncu_traffic(f'cape_{self.cfg}_{self.precision}', self.ncol)
         return {
             'bound': 'fp32', 'achieved': tf, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': tf / fp32_peak,
+            'peak_nominal': NOMINAL_FP32_TFLOPS, 'frac_of_nominal': tf / NOMINAL_FP32_TFLOPS,
             'traffic': traffic, 'traffic_unit': 'DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, scaled by columns)',
             'traffic_source': traffic_src,
-            'kernel': f'cape_kernel<MathSpec,{self.src_id},1,{str(self.p1d).lower()}>', 'kernel_ms': ms_kernel,
+            'kernel': (f'cape_kernel2<MathSpec,{self.src_id},1,{str(self.p1d).lower()}> (two columns per thread, packed FP32)'
+                       if self.precision == 'faithful' else f'cape_kernel<MathFast,{self.src_id},1,{str(self.p1d).lower()}>'), 'kernel_ms': ms_kernel,
             'work': f"{FLOP_PER_ITER:.0f} flop x {st['total_iter'] / self.ncol:.1f} moist iterations/column of the reference algorithm "
                     f"(= the faithful kernel's count); this kernel executed {st['executed_iter'] / self.ncol:.1f}/column",
             'peak_source': 'FFMA microbenchmark on this GPU (xcape_cuda_measure_peaks), 2 flop/FMA',
@@ -265,10 +304,18 @@ class SrhWorkload:
         hp['_keep'] = pin
         return hp
 
-    def step_e2e(self, hp, device):
-        a = {k: hp[k].T for k in self.KEYS3}
-        a.update({k: hp[k] for k in self.KEYS1})
-        return self._call(a, device=device)
+    def step_e2e(self, hp, device, lev_axis=-1):
+        from xcape_b200 import core
+        return core.calc_srh(*(hp[k] for k in self.KEYS3 + self.KEYS1), depth=3000, vertical_lev='sigma', output_var='srh',
+                             method='cuda', device=device, precision=self.precision, lev_axis=lev_axis)
+
+    fields3 = KEYS3
+
+    def level_major(self, hp, pin=True):
+        return CapeWorkload.level_major(self, hp, pin)
+
+    def shipped_levels(self):
+        return self.nlev
 
     def io_bytes(self):
         return int(5 * self.ncol * self.nlev * 4 + 5 * self.ncol * 4), int(16 * self.ncol)
@@ -354,9 +401,10 @@ def main():
     ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
     ap.add_argument('--workload', default='C2', choices=['C2', 'C3', 'C4', 'C5'])
     ap.add_argument('--cols', type=int, default=0, help='debug: use only the first COLS columns of the field')
-    ap.add_argument('--cpu-seconds', type=float, default=12.0, help='CPU work budget of the cpu_baseline leg')
+    ap.add_argument('--cpu-seconds', type=float, default=18.0, help='CPU work budget of the cpu_baseline leg (6 repeats in all)')
     ap.add_argument('--ref-seconds', type=float, default=3.0, help='CPU seconds per step of --impl reference')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip kernel variants, the C3/C4/C5 sub-records and the C5 stack')
     ap.add_argument('--precision', default='faithful', choices=['faithful', 'fast'],
                     help="CAPE arithmetic of every timed leg (default: faithful = bit-exact vs the oracle's SPEC mode)")
     args = ap.parse_args()
@@ -398,6 +446,18 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def time_device(fn, warm, steps):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(steps):
+            fn()
+        a1.record()
+        torch.cuda.synchronize()
+        return a0.elapsed_time(a1) / steps
 
     def max_over_ranks(x):
         if world == 1:
@@ -506,20 +566,64 @@ def main():
         del out_alt, ref_k
     st = {k: v for k, v in st.items() if not hasattr(v, 'is_cuda')}     # drop the level-major copies
 
-    # ---- end to end: pinned host buffers through the host-pointer C-ABI call ------------------
+    # ---- kernel on the adversarial / mixed fields (CAPE only): same kernel, same launch shape ---------
+    variants = None
+    if wl.kind == 'cape' and not args.no_extras and not args.cols:
+        variants = {}
+        for name, kw in (('shuffled_active', dict(shuffle=True)), ('global_mix', dict(active=False))):
+            from xcape_b200.synthetic import CONFIGS, make_soundings
+            dv = make_soundings(wl.cfg, seed=CONFIGS[wl.cfg]['seed'] + rank, winds=False,
+                                **({'grid': (721, 1440)} if wl.cfg == 'C5' else {}), **kw)
+            gv = wl.to_device(dv, dev)
+            stv = wl.kernel_state(gv)
+            ms_v = time_device(lambda: wl.step_kernel(gv, stv), 3, args.steps)
+            variants[name] = {'kernel_ms': ms_v, 'columns_per_s': ncol / (ms_v * 1e-3),
+                              'reference_iterations_per_column': stv['total_iter'] / ncol,
+                              'frac_of_fp32_peak_measured_below': None}
+            if name == 'global_mix':
+                variants[name]['gated_fraction'] = float((dv['ts'] <= 0).mean())
+            del gv, stv, dv
+        torch.cuda.empty_cache()
+
+    # ---- end to end: the public API (core.calc_cape / calc_srh, method='cuda') on host arrays -----------
     hp = wl.pinned(d)
-    for _ in range(2):
-        out_host = wl.step_e2e(hp, local_rank)
-    barrier()
+
+    def time_host(fn, warm, steps):
+        for _ in range(warm):
+            out = fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = fn()
+        torch.cuda.synchronize()
+        dt = max_over_ranks((time.perf_counter() - t0) / steps)
+        barrier()
+        return dt, out
+
     w0 = time.time()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out_host = wl.step_e2e(hp, local_rank)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
-    barrier()
+    e2e_s, out_host = time_host(lambda: wl.step_e2e(hp, local_rank), 2, args.steps)
     windows.append((w0, time.time()))
     e2e_value = world * ncol / e2e_s
+    h2d, d2h = wl.io_bytes()
+    same = all(np.array_equal(np.asarray(a), b.cpu().numpy()) for a, b in zip(out_host, out_dev))
+    e2e_extra = {}
+    # ordinary (pageable) numpy arrays: what a caller who knows nothing about pinned memory passes
+    dpage = {k: np.array(d[k], copy=True) for k in wl.fields3 + ('ps', 'ts', 'tds') + (('us', 'vs') if wl.kind == 'srh' else ())}
+    if wl.kind == 'cape' and wl.p1d:
+        dpage['p'] = d['p']
+    pg_s, out_pg = time_host(lambda: wl.step_e2e(dpage, local_rank), 2, max(3, args.steps // 2))
+    e2e_extra['pageable'] = {'value': world * ncol / pg_s, 'ms_per_step': pg_s * 1e3,
+                             'matches': bool(all(np.array_equal(a, b) for a, b in zip(out_pg, out_host)))}
+    del dpage
+    # level-major pinned arrays: the on-disk order (time, level, lat, lon) of ERA5 / HRRR files
+    hlm = wl.level_major(hp)
+    lm_s, out_lm = time_host(lambda: wl.step_e2e(hlm, local_rank, lev_axis=0), 2, args.steps)
+    ship = wl.shipped_levels()
+    e2e_extra['level_major_pinned'] = {
+        'value': world * ncol / lm_s, 'ms_per_step': lm_s * 1e3, 'levels_copied': ship, 'levels': nlev,
+        'h2d_bytes_per_step': int(h2d - (nlev - ship) * ncol * 4 * (2 if (wl.kind == 'cape' and wl.p1d) else 0)),
+        'matches': bool(all(np.array_equal(a, b) for a, b in zip(out_lm, out_host)))}
+    del hlm
     # Two host threads issuing alternate steps (what dask's threaded scheduler does with GIL-releasing
     # calls): the second call's H2D overlaps the first call's tail.  Reported next to the one-thread e2e.
     from concurrent.futures import ThreadPoolExecutor
@@ -532,15 +636,25 @@ def main():
     barrier()
     if other is not None:
         wl.precision = other['precision']
-        wl.step_e2e(hp, local_rank)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            wl.step_e2e(hp, local_rank)
-        other['e2e_ms_per_step'] = (time.perf_counter() - t0) / args.steps * 1e3
-        other['e2e_columns_per_s_this_rank'] = ncol / (other['e2e_ms_per_step'] * 1e-3)
+        o_s, _ = time_host(lambda: wl.step_e2e(hp, local_rank), 1, args.steps)
+        other['e2e_ms_per_step'] = o_s * 1e3
+        other['e2e_columns_per_s'] = world * ncol / o_s
         wl.precision = args.precision
-    h2d, d2h = wl.io_bytes()
-    same = all(np.array_equal(np.asarray(a), b.cpu().numpy()) for a, b in zip(out_host, out_dev))
+    del hp
+
+    # ---- BASELINE configs[4]: the 24-step C5 stack, 24/N steps per rank (strong scaling) ---------------
+    strong = None
+    if not args.no_extras and not args.cols and 24 % world == 0:
+        strong = strong_scaling_c5(rank, local_rank, world, dev, barrier, max_over_ranks, time_device, args)
+
+    # ---- the other named workloads as sub-records (N = 1) --------------------------------------------------
+    extras = None
+    if world == 1 and not args.no_extras and not args.cols and args.workload == 'C2':
+        extras = {}
+        shared = {}
+        for name in ('C3', 'C4', 'C5'):
+            extras[name] = sub_record(name, dev, local_rank, time_device, shared, args)
+            torch.cuda.empty_cache()
 
     gc.enable()
     clocks = sampler.stop(windows) if (rank == 0 and sampler.proc is not None) else None
@@ -553,18 +667,23 @@ def main():
         if os.path.exists(peaks_file):
             hbm_peak, hbm_src = float(json.load(open(peaks_file))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
         roofline = wl.roofline(ms_kernel, st, fp32_peak, fp64_peak, hbm_peak, hbm_src)
+        if variants:
+            for v in variants.values():
+                v['frac_of_fp32_peak'] = FLOP_PER_ITER * v['reference_iterations_per_column'] * ncol / (v['kernel_ms'] * 1e-3) / 1e12 / fp32_peak
+                v.pop('frac_of_fp32_peak_measured_below')
+        if extras:
+            for name, r in extras.items():
+                if 'reference_iterations_per_column' in r:
+                    tf = FLOP_PER_ITER * r['reference_iterations_per_column'] * r['columns'] / (r['kernel_ms'] * 1e-3) / 1e12
+                    r['roofline'] = {'bound': 'fp32', 'achieved': tf, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': tf / fp32_peak}
+                else:
+                    gbs = r['bytes_per_column'] * r['columns'] / (r['kernel_ms'] * 1e-3) / 1e9
+                    gbs_dev = r['bytes_per_column'] * r['columns'] / (r['device_path_ms_per_step'] * 1e-3) / 1e9
+                    r['roofline'] = {'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
+                                     'device_path_achieved': gbs_dev, 'device_path_frac': gbs_dev / hbm_peak}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            import oracle
-            oracle.build()
-            if full_affinity is not None:
-                os.sched_setaffinity(0, full_affinity)      # the CPU baseline gets every host core again
-            nth = host_threads()
-            r0, _, _ = wl.cpu_rate(d, min(ncol, 2000 * nth), nth)
-            sample = int(min(ncol, max(1000 * nth, r0 * args.cpu_seconds)))
-            rate, n, how = wl.cpu_rate(d, sample, nth, counters=True)
-            cpu = {'value': rate, 'unit': UNIT, 'cores': nth, 'kind': 'port',
-                   'sample': f'{n} of {ncol} columns (evenly strided) of the same field, {how}, {nth} threads'}
+            cpu = cpu_baseline(wl, d, full_affinity, args)
         line = {
             'metric': wl.metric, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
@@ -574,14 +693,18 @@ def main():
                                                      ' (FP32-pipe moist body; tolerance-level parity, MU level exact)'),
                        'l2': f'inputs {h2d / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)',
                        'parallelism': f'{world} x independent column shards, no collective',
-                       'host_numa_node_of_rank0': numa_node},
+                       'host_cpu_binding_of_rank0': numa_node},
             'ms_per_step_minmedmax': [float(np.min(per_step)), float(np.median(per_step)), float(np.max(per_step))],
             'ms_each_step': [round(float(x), 3) for x in per_step],
             'clocks': clocks, 'gpu_launches': int(launches),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': e2e_s * 1e3, 'matches_device_path': bool(same),
-                    'two_host_threads': {'value': world * ncol / e2e2_s, 'ms_per_step': e2e2_s * 1e3}},
-            'roofline': roofline, 'cpu_baseline': cpu, 'other_precision': other}
+                    'api': "core.calc_cape(method='cuda')" if wl.kind == 'cape' else "core.calc_srh(method='cuda')",
+                    'input': 'pinned host numpy, reference layout [ncol, nlev]',
+                    'h2d_gb_per_s_per_rank': h2d / e2e_s / 1e9,
+                    'two_host_threads': {'value': world * ncol / e2e2_s, 'ms_per_step': e2e2_s * 1e3}, **e2e_extra},
+            'roofline': roofline, 'cpu_baseline': cpu, 'other_precision': other, 'kernel_variants': variants,
+            'workloads': extras, 'strong_scaling_C5': strong}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
@@ -589,6 +712,122 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def cpu_baseline(wl, d, full_affinity, args):
+    """The reference algorithm (CPU oracle, glibc libm) on all host threads and on one thread: 3 repeats each on a
+    bounded, evenly strided sample of the same field; best and median."""
+    import oracle
+    oracle.build()
+    if full_affinity is not None:
+        os.sched_setaffinity(0, full_affinity)      # the CPU baseline gets every host core again
+    nth = host_threads()
+    r0, _, _ = wl.cpu_rate(d, min(wl.ncol, 2000 * nth), nth)
+    per_rep = args.cpu_seconds / 6.0                  # 3 + 3 repeats
+    out = {}
+    for label, threads, rate_guess in (('all_threads', nth, r0), ('one_thread', 1, r0 / nth)):
+        sample = int(min(wl.ncol, max(500 * threads, rate_guess * per_rep)))
+        rates, how, n = [], '', 0
+        for rep in range(3):
+            rate, n, how = wl.cpu_rate(d, sample, threads, counters=(rep == 0))
+            rates.append(rate)
+        out[label] = {'best': float(np.max(rates)), 'median': float(np.median(rates)), 'threads': threads,
+                      'columns_per_repeat': n, 'repeats': 3, 'how': how}
+    best = out['all_threads']
+    return {'value': best['best'], 'unit': UNIT, 'cores': nth, 'kind': 'port',
+            'sample': f"{best['columns_per_repeat']} of {wl.ncol} columns (evenly strided) of the same field, best of 3 repeats, "
+                      f"{best['how']}, {nth} threads",
+            'median': best['median'], 'one_thread': out['one_thread'],
+            'why_port': 'the reference is Fortran: no Fortran compiler here or on the GPU box (probed: gfortran / flang / nvfortran / ifx '
+                        'absent, only the libgfortran runtime inside numpy/scipy wheels), so the CPU arm is the line-by-line C++ oracle'}
+
+
+def sub_record(name, dev, local_rank, time_device, shared, args):
+    """One of the other BASELINE workloads on this GPU: kernel alone, device path in the reference layout, e2e."""
+    import torch
+    wl = get_workload(name)
+    wl.precision = 'faithful'
+    from xcape_b200.synthetic import CONFIGS, make_soundings
+    if name in ('C3', 'C4'):                       # same grid and seed: generate once, with winds
+        if 'hrrr' not in shared:
+            shared['hrrr'] = make_soundings('C4', seed=CONFIGS['C4']['seed'])
+        d = shared['hrrr']
+        wl.ncol, wl.nlev = d['t'].shape
+        if wl.kind == 'cape':
+            wl.p1d = False
+            wl.fields3 = ('p', 't', 'td')
+            wl.roofline_launches = 1
+            wl.bytes_per_col = 4.0 * (3 * wl.nlev) + 12 + 8
+        else:
+            wl.bytes_per_col = 4.0 * (5 * wl.nlev) + 20 + 8
+    else:
+        d = wl.make(0, 0)
+    g = wl.to_device(d, dev)
+    steps = max(3, min(args.steps, 5))
+    ms_dev = time_device(lambda: wl.step_dev(g), 3, steps)
+    st = wl.kernel_state(g)
+    ms_k = time_device(lambda: wl.step_kernel(g, st), 2, steps)
+    rec = {'workload': wl.workload, 'columns': int(wl.ncol), 'levels': int(wl.nlev), 'kernel_ms': ms_k,
+           'kernel_columns_per_s': wl.ncol / (ms_k * 1e-3), 'device_path_ms_per_step': ms_dev,
+           'device_path_columns_per_s': wl.ncol / (ms_dev * 1e-3), 'bytes_per_column': wl.bytes_per_col}
+    if wl.kind == 'cape':
+        rec['reference_iterations_per_column'] = st['total_iter'] / wl.ncol
+    else:
+        wl.precision = 'fast'
+        rec['fast_heights_kernel_ms'] = time_device(lambda: wl.step_kernel(g, st), 2, steps)
+        wl.precision = 'faithful'
+    del st
+    hp = wl.pinned(d)
+    wl.step_e2e(hp, local_rank)
+    t0 = time.perf_counter()
+    for _ in range(2):
+        wl.step_e2e(hp, local_rank)
+    torch.cuda.synchronize()
+    e2e = (time.perf_counter() - t0) / 2
+    h2d, d2h = wl.io_bytes()
+    rec['e2e'] = {'value': wl.ncol / e2e, 'ms_per_step': e2e * 1e3, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h}
+    del hp, g
+    return rec
+
+
+def strong_scaling_c5(rank, local_rank, world, dev, barrier, max_over_ranks, time_device, args):
+    """24 time steps of 721 x 1440 x 137 (most-unstable), column-sharded by time step: 24 / N steps per rank.  Each
+    rank holds ONE synthetic step (seed folded with its rank) and runs it 24 / N times — the arithmetic and the bytes
+    moved are those of the stack, the host does not spend minutes generating 41 GB of soundings."""
+    import torch
+    wl = get_workload('C5')
+    wl.precision = args.precision
+    d = wl.make(rank, 0)
+    g = wl.to_device(d, dev)
+    mine = 24 // world
+    wl.step_dev(g)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(mine):
+        out = wl.step_dev(g)
+    e1.record()
+    barrier()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    del g, out
+    torch.cuda.empty_cache()
+    hlm = wl.level_major(d)                          # pinned, in the stack's on-disk order: (time, level, lat, lon)
+    wl.step_e2e(hlm, local_rank, lev_axis=0)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(mine):
+        wl.step_e2e(hlm, local_rank, lev_axis=0)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    h2d, d2h = wl.io_bytes()
+    total = 24 * wl.ncol
+    return {'workload': 'calc_cape most-unstable on the 24-step 721x1440x137 stack (configs[4]), 24/N steps per GPU',
+            'scaling': 'strong', 'steps_total': 24, 'steps_per_rank': mine, 'columns_total': total, 'levels': wl.nlev,
+            'device_resident': {'ms_total': ms_dev, 'value': total / (ms_dev * 1e-3), 'unit': UNIT},
+            'e2e': {'ms_total': e2e_s * 1e3, 'value': total / e2e_s, 'unit': UNIT, 'input': 'pinned host numpy, level-major [nlev, ncol]',
+                    'h2d_bytes_total': h2d * 24, 'h2d_gb_per_s_per_rank': h2d * mine / e2e_s / 1e9},
+            'data': 'each rank re-uses one synthetic 721x1440x137 step for its 24/N steps'}
 
 
 if __name__ == '__main__':

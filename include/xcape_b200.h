@@ -152,6 +152,11 @@ XCAPE_API const char* xcape_cuda_last_error(void);      /* thread-local message 
 XCAPE_API int xcape_cuda_device_count(void);            /* < 0 on error */
 XCAPE_API const char* xcape_cuda_version(void);         /* "xcape_b200 <semver> sm_100a" */
 XCAPE_API int64_t xcape_cuda_kernel_launches(void);     /* kernels launched by this library so far (process-wide) */
+/* xcape_cuda_cape with HOST pointers on a shared pressure axis copies only the levels the ascent can reach (up to the
+ * first one with p <= 100 hPa, where the reference stops a negatively buoyant parcel, CAPE_CODE_model_lev.f90:554-557);
+ * columns still ascending there are redone with every level.  This counts those columns (process-wide).
+ * XCAPE_B200_SHIP_ALL_LEVELS=1 in the environment disables the optimisation. */
+XCAPE_API int64_t xcape_cuda_columns_redone(void);
 /* The library keeps its stream-ordered scratch (relayout buffers, staging blocks) in a private
  * cudaMemPool per device and never returns it to the driver on its own (re-mapping ~300 MB per call cost
  * 5 ms per ERA5 field).  This call synchronises `device` and hands the cached memory back, along

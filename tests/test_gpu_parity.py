@@ -212,6 +212,80 @@ def test_float64_or_integer_1d_arguments_next_to_float32_fields(core, top_first)
             assert np.array_equal(g, r)
 
 
+@pytest.mark.parametrize('lev_axis,top_first', [(-1, False), (0, False), (0, True), (-1, True)])
+def test_host_path_ships_only_reachable_levels_and_redoes_overshooting_columns(core, oracle_mod, lev_axis, top_first, monkeypatch):
+    """Host inputs on a pressure grid: only the levels up to the first one with p <= 100 hPa are copied to the GPU;
+    columns whose parcel is still buoyant there come back flagged and are redone with every level.  Same bits as
+    shipping everything, as the device-pointer path and as the oracle — on a field where 1 column in 7 overshoots."""
+    import torch
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C2', cols=(200_000, 230_001))
+    t, td = d['t'].copy(), d['td'].copy()
+    hot = np.arange(t.shape[0]) % 7 == 3
+    lev = d['p']
+    t[np.ix_(hot, np.flatnonzero(lev <= 150.0))] -= 45.0       # a very cold upper troposphere / stratosphere: the parcel overshoots 100 hPa
+    td = np.minimum(td, t - 1.0)
+    p = lev.copy()
+    if top_first:
+        p, t, td = p[::-1].copy(), t[:, ::-1].copy(), td[:, ::-1].copy()
+    if lev_axis == 0:
+        t, td = np.ascontiguousarray(t.T), np.ascontiguousarray(td.T)
+    kw = dict(source='most-unstable', pinc=500., vertical_lev='pressure', lev_axis=lev_axis,
+              level_order='top_first' if top_first else 'surface_first')
+    args = (p, t, td, d['ps'], d['ts'], d['tds'])
+    from xcape_b200 import _lib
+    n0 = _lib.columns_redone()
+    got = core.calc_cape(*args, **kw)
+    redone = _lib.columns_redone() - n0
+    assert 1000 < redone <= hot.sum()                  # only (and most of) the chilled columns took the second pass
+    monkeypatch.setenv('XCAPE_B200_SHIP_ALL_LEVELS', '1')
+    full = core.calc_cape(*args, **kw)
+    monkeypatch.delenv('XCAPE_B200_SHIP_ALL_LEVELS')
+    assert _lib.columns_redone() - n0 == redone        # nothing is redone when every level is shipped
+    dev = core.calc_cape(*(torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in args), **kw)
+    for g, f, v in zip(got, full, dev):
+        assert np.array_equal(g, f) and np.array_equal(g, v.cpu().numpy())
+    okw = dict(source='most-unstable', pinc=500., vertical_lev='pressure')
+    tt = t.T if lev_axis == 0 else t
+    tdd = td.T if lev_axis == 0 else td
+    if top_first:
+        tt, tdd = tt[:, ::-1], tdd[:, ::-1]
+    ref = oracle_mod.calc_cape_ref(lev, np.ascontiguousarray(tt), np.ascontiguousarray(tdd), d['ps'], d['ts'], d['tds'],
+                                   tmode=oracle_mod.SPEC, nthreads=8, **okw)
+    assert_bitexact(got, ref, 'level-window host path')
+
+
+def test_explicit_stream_with_prepared_temporaries(core):
+    """`stream=` with CUDA tensors whose preparation (float64 -> float32 casts, strided -> dense copies,
+    output allocation) runs on torch's current stream: the kernels on the user's stream must wait for it, and the
+    temporaries must not be recycled under them.  A busy current stream in front makes a missing dependency show."""
+    import torch
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C3', cols=(0, 200_000))
+    dev = torch.device('cuda', 0)
+    g = {k: torch.from_numpy(d[k]).to(dev) for k in ('p', 't', 'td', 'u', 'v', 'ps', 'ts', 'tds', 'us', 'vs')}
+    kw = dict(source='mixed-layer', ml_depth=500., pinc=500., vertical_lev='sigma')
+    ref = core.calc_cape(g['p'], g['t'], g['td'], g['ps'], g['ts'], g['tds'], **kw)
+    sref = core.calc_srh(*(g[k] for k in ('p', 't', 'td', 'u', 'v', 'ps', 'ts', 'tds', 'us', 'vs')), vertical_lev='sigma')
+    torch.cuda.synchronize()
+    g64 = {k: v.double() for k, v in g.items()}          # float64 inputs: every field is cast on the device first
+    side = torch.cuda.Stream(device=dev)
+    junk = torch.empty(64 << 20, device=dev)
+    for rep in range(3):
+        for _ in range(20):
+            junk.normal_()                                  # keep the current stream busy ahead of the preparation
+        got = core.calc_cape(g64['p'], g64['t'], g64['td'], g64['ps'], g64['ts'], g64['tds'], stream=side.cuda_stream, **kw)
+        sgot = core.calc_srh(*(g64[k] for k in ('p', 't', 'td', 'u', 'v', 'ps', 'ts', 'tds', 'us', 'vs')), vertical_lev='sigma',
+                             stream=side.cuda_stream)
+        scratch = [torch.full((200_000 * 50,), float(rep), device=dev) for _ in range(6)]   # would overwrite recycled temporaries
+        side.synchronize()
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b)
+        for a, b in zip(sgot, sref):
+            assert (a - b).abs().max().item() < 1e-6
+        del scratch
+
+
 def test_c5_shape_137_levels_bitexact(core, oracle_mod):
     from xcape_b200.synthetic import make_soundings
     d = make_soundings('C5', cols=(0, 6000))

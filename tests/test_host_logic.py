@@ -196,3 +196,31 @@ def test_cpulist_parsing_and_numa_binding_is_harmless_without_a_gpu():
     before = os.sched_getaffinity(0)
     assert bind_host_to_gpu(0) is None            # no CUDA device here: nothing changes
     assert os.sched_getaffinity(0) == before
+
+
+def test_gpu_cpu_affinity_from_nvidia_smi_topo():
+    """bench.py / sharding bind a rank to the CPUs next to its GPU; where sysfs hides the NUMA node (containers)
+    the set comes from `nvidia-smi topo -m`."""
+    from xcape_b200.sharding import format_cpulist, gpu_cpu_affinity, parse_cpulist
+    txt = ("\t\x1b[4mGPU0\tGPU1\tNIC0\tCPU Affinity\tNUMA Affinity\tGPU NUMA ID\x1b[0m\n"
+           "GPU0\t X \tNV18\tSYS\t0-15,64-79\t0\t\tN/A\nGPU1\tNV18\t X \tPIX\t16-31\t1\t\tN/A\n"
+           "NIC0\tSYS\tPIX\t X \t\t\t\t\n\nLegend:\n  X = Self\n")
+    assert gpu_cpu_affinity(0, txt) == parse_cpulist('0-15,64-79')
+    assert format_cpulist(gpu_cpu_affinity(1, txt)) == '16-31'
+    assert gpu_cpu_affinity(2, txt) is None and gpu_cpu_affinity(0, 'garbage') is None
+    assert format_cpulist({0, 1, 2, 5, 7, 8}) == '0-2,5,7-8'
+
+
+def test_level_order_auto_skips_masked_columns_and_raises_when_undetermined():
+    """'auto' used to read column 0 only — a NaN / fill value there made a top-first field run upside-down."""
+    p = np.linspace(1000, 100, 10)
+    assert core._top_first(p, -1, 'auto') is False and core._top_first(p[::-1], -1, 'auto') is True
+    P = np.broadcast_to(p, (5, 7, 10)).copy()
+    P[0, 0, :] = np.nan                               # first column masked
+    P[0, 1, :] = 9.96921e36                           # second column a fill value
+    assert core._top_first(P, -1, 'auto') is False and core._top_first(P[..., ::-1], -1, 'auto') is True
+    assert core._top_first(np.moveaxis(P[..., ::-1], -1, 0), 0, 'auto') is True
+    with pytest.raises(ValueError):
+        core._top_first(np.full((3, 4), np.nan), -1, 'auto')
+    with pytest.raises(ValueError):
+        core._top_first(np.array([500., 500.]), -1, 'auto')

@@ -103,6 +103,25 @@ def stream_of(ref, stream=None):
     return None
 
 
+def order_on_stream(ref, stream, tensors):
+    """An explicit ``stream=`` with CUDA tensors: everything the shim prepared (casts, relayouts, start levels, the
+    freshly allocated outputs) was produced on torch's CURRENT stream, while the kernels are enqueued on the
+    caller's stream.  Make the caller's stream wait for the preparation, and tell torch's caching allocator that
+    those tensors are in use on it — otherwise a temporary could be read before it is written, or be recycled
+    while the kernel is still running."""
+    if stream is None or not is_cuda(ref):
+        return
+    import torch
+    cur = torch.cuda.current_stream(ref.device)
+    if int(stream) == int(cur.cuda_stream):
+        return
+    ext = torch.cuda.ExternalStream(int(stream), device=ref.device)
+    ext.wait_stream(cur)
+    for t in tensors:
+        if t is not None and is_cuda(t):
+            t.record_stream(ext)
+
+
 def device_of(ref, device):
     if is_cuda(ref):
         return ref.device.index if ref.device.index is not None else 0

@@ -22,7 +22,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_NODEV = 0, 1, 2, 3
 SYMBOLS = ('xcape_cuda_cape', 'xcape_cuda_srh', 'xcape_cuda_srh_from_heights', 'xcape_cuda_stdheight', 'xcape_cuda_pres_lev_pos',
            'xcape_cuda_last_error', 'xcape_cuda_device_count', 'xcape_cuda_version',
            'xcape_cuda_kernel_launches', 'xcape_cuda_measure_peaks', 'xcape_cuda_release_memory',
-           'xcape_cuda_dewpoint_from_q')
+           'xcape_cuda_dewpoint_from_q', 'xcape_cuda_columns_redone')
 
 _lib = None
 
@@ -65,6 +65,7 @@ def lib():
         L.xcape_cuda_version.restype = C.c_char_p
         L.xcape_cuda_device_count.restype = i32
         L.xcape_cuda_kernel_launches.restype = i64
+        L.xcape_cuda_columns_redone.restype = i64
         L.xcape_cuda_release_memory.restype = i32
         L.xcape_cuda_release_memory.argtypes = [i32]
         L.xcape_cuda_measure_peaks.restype = i32
@@ -83,6 +84,11 @@ def check(rc):
 
 def kernel_launches():
     return int(lib().xcape_cuda_kernel_launches())
+
+
+def columns_redone():
+    """Columns the host path of ``xcape_cuda_cape`` redid with all levels so far (see include/xcape_b200.h)."""
+    return int(lib().xcape_cuda_columns_redone())
 
 
 def measure_peaks(device=0, reps=5):

@@ -98,6 +98,8 @@ def cape(p_2d, t_2d, td_2d, p_s, t_s, td_s, flag_1d, pres_lev_pos, source, ml_de
     st_o = A.empty_like_host_or_device(ref, (ngrid,), 'int32') if (return_status or return_counters) else None
     it_o = A.empty_like_host_or_device(ref, (ngrid,), 'int32') if return_counters else None
 
+    A.order_on_stream(ref, stream, [p, t_, td_, ps_, ts_, tds_, start, cape_o, cin_o, mu_o, z_o, st_o, it_o])
+
     def call(c0, c1, dev):
         n = c1 - c0
         if n <= 0:
@@ -156,6 +158,7 @@ def pres_lev_pos(p_1d, p_s, *, device=0, stream=None):
     ps_ = A.dense_1d(A.cast(p_s, dt))
     n = ps_.shape[0]
     out = A.empty_like_host_or_device(ps_, (n,), 'int32')
+    A.order_on_stream(ps_, stream, [p, ps_, out])
     rc = L.xcape_cuda_pres_lev_pos(A.ptr(p), A.ptr(ps_), C.c_int64(n), int(p.shape[0]),
                                    _lib.F32 if dt == 'float32' else _lib.F64,
                                    _lib.MEM_DEVICE if all(on_dev) else _lib.MEM_HOST, A.ptr(out),

@@ -107,15 +107,26 @@ def _top_first(p, lev_axis, level_order):
         raise ValueError(f"`level_order` must be one of: {list(_LEVEL_ORDERS)}")
     if level_order != 'auto':
         return level_order == 'top_first'
+    if A.is_torch(p):
+        p = p.detach()
     if p.ndim == 1:
-        first, last = p[0], p[-1]
-    elif lev_axis == 0:
-        col = p.reshape(p.shape[0], -1)
-        first, last = col[0, 0], col[-1, 0]
+        first, last = float(p[0]), float(p[-1])
     else:
-        col = p.reshape(-1, p.shape[-1])
-        first, last = col[0, 0], col[0, -1]
-    return bool(float(first) < float(last))
+        # first / last level of a column whose two values are both finite (masked points carry NaN or fill values):
+        # look at a bounded sample of columns rather than at column 0 only
+        col = p.reshape(p.shape[0], -1) if lev_axis == 0 else p.reshape(-1, p.shape[-1]).T
+        ncol = col.shape[1]
+        idx = np.unique(np.linspace(0, ncol - 1, num=min(ncol, 257)).astype(np.int64))
+        lo, hi = col[0][idx], col[-1][idx]
+        lo, hi = (np.asarray(x.cpu() if A.is_torch(x) else x, dtype=np.float64) for x in (lo, hi))
+        ok = np.isfinite(lo) & np.isfinite(hi) & (np.abs(lo) < 1e6) & (np.abs(hi) < 1e6) & (lo != hi)
+        if not ok.any():
+            raise ValueError("level_order='auto': no column with finite, distinct first and last pressures in the sample; "
+                             "pass level_order='surface_first' or 'top_first'")
+        first, last = float(lo[ok][0]), float(hi[ok][0])
+    if not (np.isfinite(first) and np.isfinite(last)) or first == last:
+        raise ValueError("level_order='auto': the pressure axis does not determine the order; pass level_order explicitly")
+    return bool(first < last)
 
 
 def _any_dask_array(*args):

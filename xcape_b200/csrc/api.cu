@@ -20,6 +20,7 @@ namespace xc {
 
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
+std::atomic<int64_t> g_redone{0};       // columns the host path handed back for a second pass with all levels
 
 namespace {
 
@@ -146,10 +147,11 @@ int cape_device(const void* p, const void* t, const void* td, const void* ps, co
                 int64_t ncol, int nlev, int p_is_1d, int dtype, int layout, int64_t ld_in,
                 int source, int adiabat, float ml_depth, float pinc, const int32_t* start_3d,
                 float* cape, float* cin, int32_t* mulev, float* zmulev, int32_t* status, int32_t* n_iter,
-                int precision, cudaStream_t s) {
+                int precision, cudaStream_t s, bool more_levels = false) {
   if (ncol == 0) return XCAPE_OK;
   Scratch sc(s);
   CapeArgs a{};
+  a.more_levels = more_levels ? 1 : 0;
   int rc;
   int64_t ld = ncol, ldp = ncol;
   const float* q;
@@ -171,7 +173,7 @@ int cape_device(const void* p, const void* t, const void* td, const void* ps, co
   if (p_is_1d && !start_3d) {
     int32_t* st;
     XC_CUDA(sc.alloc(&st, (size_t)ncol));
-    if ((rc = launch_pres_lev_pos(p, ps, dtype, ncol, nlev, st, s))) return rc;   // in the inputs' own dtype
+    if ((rc = launch_pres_lev_pos(p, ps, dtype, ncol, nlev, st, s, more_levels ? 0 : 1))) return rc;   // in the inputs' own dtype
     a.start = st;
   }
   if (p_is_1d) {          // Exner function of the shared pressure axis, once per call
@@ -322,12 +324,16 @@ struct Block {
   void* p1d = nullptr;
 };
 
+// Stored levels [l0, l0 + nl) of columns [c0, c0 + n) of a 3-D host field -> dense [n][nl] / [nl][n] block on the device.
 cudaError_t h2d_field(void* dst, const void* src, int layout, int64_t ncol, int nlev, int64_t c0, int64_t n, size_t es,
-                      cudaStream_t s) {
-  if (layout == XCAPE_LEVEL_LAST)
-    return cudaMemcpyAsync(dst, (const char*)src + (size_t)c0 * nlev * es, (size_t)n * nlev * es, cudaMemcpyHostToDevice, s);
-  return cudaMemcpy2DAsync(dst, (size_t)n * es, (const char*)src + (size_t)c0 * es, (size_t)ncol * es, (size_t)n * es,
-                           (size_t)nlev, cudaMemcpyHostToDevice, s);
+                      cudaStream_t s, int l0, int nl) {
+  if (layout == XCAPE_LEVEL_LAST) {
+    const char* from = (const char*)src + ((size_t)c0 * nlev + l0) * es;
+    if (nl == nlev) return cudaMemcpyAsync(dst, from, (size_t)n * nlev * es, cudaMemcpyHostToDevice, s);
+    return cudaMemcpy2DAsync(dst, (size_t)nl * es, from, (size_t)nlev * es, (size_t)nl * es, (size_t)n, cudaMemcpyHostToDevice, s);
+  }
+  return cudaMemcpy2DAsync(dst, (size_t)n * es, (const char*)src + ((size_t)l0 * ncol + c0) * es, (size_t)ncol * es, (size_t)n * es,
+                           (size_t)nl, cudaMemcpyHostToDevice, s);
 }
 cudaError_t d2h_field(void* dst, const void* src, int layout, int64_t ncol, int nlev, int64_t c0, int64_t n, size_t es,
                       cudaStream_t s) {
@@ -337,34 +343,60 @@ cudaError_t d2h_field(void* dst, const void* src, int layout, int64_t ncol, int 
                            cudaMemcpyDeviceToHost, s);
 }
 
-// Pinned host staging buffers, cached process-wide (cudaHostAlloc costs milliseconds).
+// Pinned host staging buffers, cached process-wide (cudaHostAlloc costs milliseconds).  Best fit with a slack limit
+// (a small request must not occupy a buffer several times its size), and a cap on what stays cached: idle buffers
+// are freed least-recently-used first once the total exceeds XCAPE_B200_PINNED_CACHE_BYTES (default 8 GiB), so a
+// long-running worker that sees many shapes does not grow page-locked memory without bound.
 struct PinnedCache {
-  struct Ent { void* p; size_t bytes; bool used; };
+  struct Ent { void* p; size_t bytes; bool used; uint64_t stamp; };
   std::mutex mu;
   std::vector<Ent> ents;
+  uint64_t clock = 0;
+  size_t total = 0;
+  static size_t cap() { return (size_t)env_i64("XCAPE_B200_PINNED_CACHE_BYTES", (int64_t)8 << 30, 0, (int64_t)1 << 46); }
   void* acquire(size_t bytes) {
+    bytes = std::max<size_t>(bytes, 1);
     std::lock_guard<std::mutex> lk(mu);
+    Ent* best = nullptr;
     for (auto& e : ents)
-      if (!e.used && e.bytes >= bytes) { e.used = true; return e.p; }
+      if (!e.used && e.bytes >= bytes && e.bytes <= 2 * bytes + ((size_t)1 << 20) && (!best || e.bytes < best->bytes)) best = &e;
+    if (best) { best->used = true; best->stamp = ++clock; return best->p; }
+    evict_locked(bytes);
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    ents.push_back({p, bytes, true});
+    ents.push_back({p, bytes, true, ++clock});
+    total += bytes;
     return p;
   }
   void release(void* p) {
     std::lock_guard<std::mutex> lk(mu);
     for (auto& e : ents)
-      if (e.p == p) e.used = false;
+      if (e.p == p) { e.used = false; e.stamp = ++clock; }
+    evict_locked(0);
+  }
+  // free idle entries, oldest first, until `incoming` more bytes fit under the cap
+  void evict_locked(size_t incoming) {
+    const size_t limit = cap();
+    while (total + incoming > limit) {
+      int victim = -1;
+      for (int i = 0; i < (int)ents.size(); ++i)
+        if (!ents[i].used && (victim < 0 || ents[i].stamp < ents[victim].stamp)) victim = i;
+      if (victim < 0) break;
+      cudaFreeHost(ents[victim].p);
+      total -= ents[victim].bytes;
+      ents.erase(ents.begin() + victim);
+    }
   }
   void trim() {                                   // give idle buffers back (xcape_cuda_release_memory)
     std::lock_guard<std::mutex> lk(mu);
     std::vector<Ent> kept;
     for (auto& e : ents) {
       if (e.used) kept.push_back(e);
-      else cudaFreeHost(e.p);
+      else { cudaFreeHost(e.p); total -= e.bytes; }
     }
     ents.swap(kept);
   }
+  size_t cached_bytes() { std::lock_guard<std::mutex> lk(mu); return total; }
 };
 PinnedCache g_pinned;
 
@@ -396,12 +428,21 @@ void parallel_memcpy(void* dst, const void* src, size_t bytes) {
   });
 }
 
-// columns [c0, c0+n) of a 3-D host field -> dense block of the same layout in `dst` (host)
-void stage_field(void* dst, const void* src, int layout, int64_t ncol, int nlev, int64_t c0, int64_t n, size_t es) {
-  if (layout == XCAPE_LEVEL_LAST) { parallel_memcpy(dst, (const char*)src + (size_t)c0 * nlev * es, (size_t)n * nlev * es); return; }
-  auto row = [=](int k) { memcpy((char*)dst + (size_t)k * n * es, (const char*)src + ((size_t)k * ncol + c0) * es, (size_t)n * es); };
-  if ((size_t)n * nlev * es < ((size_t)4 << 20)) { for (int k = 0; k < nlev; ++k) row(k); return; }
-  parallel_parts(nlev, row);                       // level-major: one row of the block per level
+// stored levels [l0, l0 + nl) of columns [c0, c0+n) of a 3-D host field -> dense block of the same layout in `dst` (host)
+void stage_field(void* dst, const void* src, int layout, int64_t ncol, int nlev, int64_t c0, int64_t n, size_t es, int l0, int nl) {
+  if (layout == XCAPE_LEVEL_LAST) {
+    const char* from = (const char*)src + ((size_t)c0 * nlev + l0) * es;
+    if (nl == nlev) { parallel_memcpy(dst, from, (size_t)n * nlev * es); return; }
+    const int64_t per = 8192;                      // columns per work item: compact each column's window
+    parallel_parts((int)((n + per - 1) / per), [=](int q) {
+      const int64_t a = (int64_t)q * per, b = std::min<int64_t>(n, a + per);
+      for (int64_t c = a; c < b; ++c) memcpy((char*)dst + (size_t)c * nl * es, from + (size_t)c * nlev * es, (size_t)nl * es);
+    });
+    return;
+  }
+  auto row = [=](int k) { memcpy((char*)dst + (size_t)k * n * es, (const char*)src + ((size_t)(l0 + k) * ncol + c0) * es, (size_t)n * es); };
+  if ((size_t)n * nl * es < ((size_t)4 << 20)) { for (int k = 0; k < nl; ++k) row(k); return; }
+  parallel_parts(nl, row);                         // level-major: one row of the block per level
 }
 
 bool is_pageable_host(const void* p) {
@@ -442,12 +483,16 @@ struct RingPool {
 RingPool g_rings;
 
 // A D2H copy into PAGEABLE memory blocks the host until the producing kernel has finished, which
-// would serialise the ring (r1c probe: one block per field was faster than four).  Per-column
-// outputs are therefore landed in a pinned staging slot per stream and copied to the caller's
-// arrays by the host once the slot's event fires — while later blocks are still running.
+// would serialise the ring (r1c probe: one block per field was faster than four).  Outputs — per-column
+// ones and 3-D fields (stdheight's h, dewpoint_from_q's td) alike — are therefore landed in a pinned
+// staging slot per stream and copied to the caller's arrays by the host once the slot's event fires,
+// while later blocks are still running.
+// `l0`, `nl`: window of STORED levels of the 3-D inputs (and of the shared pressure axis) that is shipped; the launch
+// callback then sees nl-level blocks.  Calls with 3-D outputs ship every level.
 template <class F>
 int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_host, const std::vector<HostIn3>& in3,
-               const std::vector<HostIn1>& in1, const std::vector<HostOut>& outs, F launch) {
+               const std::vector<HostIn1>& in1, const std::vector<HostOut>& outs, F launch, int l0 = 0, int nl = -1) {
+  if (nl < 0) nl = nlev;
   const int64_t chunk = std::min<int64_t>(ncol, chunk_cols());          // capacity of a slot
   const int64_t first = std::min<int64_t>(chunk, first_chunk_cols());
   // block plan: geometric ramp, then full blocks; a short remainder is shared with its predecessor so that
@@ -479,7 +524,7 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
   for (size_t k = 0; k < in1.size(); ++k) in1_pageable[k] = stage_inputs && is_pageable_host(in1[k].host);
   std::vector<char> staged(outs.size(), 0);
   for (size_t k = 0; k < outs.size(); ++k)
-    staged[k] = (outs[k].host && !outs[k].is3d && is_pageable_host(outs[k].host)) ? 1 : 0;
+    staged[k] = (outs[k].host && is_pageable_host(outs[k].host)) ? 1 : 0;        // per-column AND 3-D outputs
 
   const bool trace = getenv("XCAPE_B200_TRACE") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -487,9 +532,17 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
   auto drain = [&](int i) -> int {                // wait for slot i's block, hand its outputs to the caller
     if (!pend[i].on) return XCAPE_OK;
     XC_CUDA(cudaEventSynchronize(done[i]));
-    for (size_t k = 0; k < outs.size(); ++k)
-      if (staged[k])
-        memcpy((char*)outs[k].host + (size_t)pend[i].c0 * outs[k].bytes_per_col, stage[i][k], (size_t)pend[i].n * outs[k].bytes_per_col);
+    for (size_t k = 0; k < outs.size(); ++k) {
+      if (!staged[k]) continue;
+      const size_t bpc = outs[k].bytes_per_col;
+      const int64_t c0 = pend[i].c0, n = pend[i].n;
+      if (!outs[k].is3d) { memcpy((char*)outs[k].host + (size_t)c0 * bpc, stage[i][k], (size_t)n * bpc); continue; }
+      // a 3-D field in the inputs' layout: the slot holds the dense [n][nlev] / [nlev][n] block
+      if (layout == XCAPE_LEVEL_LAST) parallel_memcpy((char*)outs[k].host + (size_t)c0 * nlev * bpc, stage[i][k], (size_t)n * nlev * bpc);
+      else parallel_parts(nlev, [&](int lev) {
+        memcpy((char*)outs[k].host + ((size_t)lev * ncol + c0) * bpc, (const char*)stage[i][k] + (size_t)lev * n * bpc, (size_t)n * bpc);
+      });
+    }
     pend[i].on = false;
     return XCAPE_OK;
   };
@@ -511,9 +564,9 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
       st[i] = ring->st[i];
       done[i] = ring->ev[i];
       for (size_t k = 0; k < in3.size(); ++k) {
-        void* q; XC_CUDA(pool_alloc(&q, (size_t)chunk * nlev * es, st[i])); b[i].in3.push_back(q);
+        void* q; XC_CUDA(pool_alloc(&q, (size_t)chunk * nl * es, st[i])); b[i].in3.push_back(q);
         void* h = nullptr;
-        if (in3_pageable[k] && !(h = g_pinned.acquire((size_t)chunk * nlev * es))) return fail(XCAPE_ERR_CUDA, "cudaHostAlloc failed (input staging)");
+        if (in3_pageable[k] && !(h = g_pinned.acquire((size_t)chunk * nl * es))) return fail(XCAPE_ERR_CUDA, "cudaHostAlloc failed (input staging)");
         stage3[i].push_back(h);
       }
       for (size_t k = 0; k < in1.size(); ++k) {
@@ -527,14 +580,14 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
         b[i].out.push_back(q);
         void* h = nullptr;
         if (staged[k]) {
-          h = g_pinned.acquire((size_t)chunk * outs[k].bytes_per_col);
+          h = g_pinned.acquire((size_t)chunk * (outs[k].is3d ? (size_t)nlev : 1) * outs[k].bytes_per_col);
           if (!h) return fail(XCAPE_ERR_CUDA, "cudaHostAlloc failed for the output staging buffer");
         }
         stage[i].push_back(h);
       }
       if (p1d_host) {
-        XC_CUDA(pool_alloc(&b[i].p1d, (size_t)nlev * es, st[i]));
-        XC_CUDA(cudaMemcpyAsync(b[i].p1d, p1d_host, (size_t)nlev * es, cudaMemcpyHostToDevice, st[i]));
+        XC_CUDA(pool_alloc(&b[i].p1d, (size_t)nl * es, st[i]));
+        XC_CUDA(cudaMemcpyAsync(b[i].p1d, (const char*)p1d_host + (size_t)l0 * es, (size_t)nl * es, cudaMemcpyHostToDevice, st[i]));
       }
     }
     if (trace) fprintf(stderr, "[xcape_b200]   setup done at %.3f ms\n", now() - t_begin);
@@ -552,10 +605,10 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
       }
       for (size_t k = 0; k < in3.size(); ++k) {
         if (stage3[i][k]) {        // pageable: host threads fill the slot's pinned buffer, then a true async H2D
-          stage_field(stage3[i][k], in3[k].host, layout, ncol, nlev, c0, n, es);
-          XC_CUDA(cudaMemcpyAsync(b[i].in3[k], stage3[i][k], (size_t)n * nlev * es, cudaMemcpyHostToDevice, s));
+          stage_field(stage3[i][k], in3[k].host, layout, ncol, nlev, c0, n, es, l0, nl);
+          XC_CUDA(cudaMemcpyAsync(b[i].in3[k], stage3[i][k], (size_t)n * nl * es, cudaMemcpyHostToDevice, s));
         } else {
-          XC_CUDA(h2d_field(b[i].in3[k], in3[k].host, layout, ncol, nlev, c0, n, es, s));
+          XC_CUDA(h2d_field(b[i].in3[k], in3[k].host, layout, ncol, nlev, c0, n, es, s, l0, nl));
         }
       }
       for (size_t k = 0; k < in1.size(); ++k) {
@@ -568,7 +621,8 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
       if (trace) mark(&tl.back().e[2], s);
       for (size_t k = 0; k < outs.size(); ++k) {
         if (!outs[k].host) continue;
-        if (outs[k].is3d) XC_CUDA(d2h_field(outs[k].host, b[i].out[k], layout, ncol, nlev, c0, n, outs[k].bytes_per_col, s));
+        if (outs[k].is3d && staged[k]) XC_CUDA(cudaMemcpyAsync(stage[i][k], b[i].out[k], (size_t)n * nlev * outs[k].bytes_per_col, cudaMemcpyDeviceToHost, s));
+        else if (outs[k].is3d) XC_CUDA(d2h_field(outs[k].host, b[i].out[k], layout, ncol, nlev, c0, n, outs[k].bytes_per_col, s));
         else if (staged[k]) XC_CUDA(cudaMemcpyAsync(stage[i][k], b[i].out[k], (size_t)n * outs[k].bytes_per_col, cudaMemcpyDeviceToHost, s));
         else XC_CUDA(cudaMemcpyAsync((char*)outs[k].host + (size_t)c0 * outs[k].bytes_per_col, b[i].out[k], (size_t)n * outs[k].bytes_per_col, cudaMemcpyDeviceToHost, s));
       }
@@ -628,6 +682,7 @@ extern "C" {
 const char* xcape_cuda_last_error(void) { return g_last_error.c_str(); }
 const char* xcape_cuda_version(void) { return "xcape_b200 0.1.0 sm_100a"; }
 int64_t xcape_cuda_kernel_launches(void) { return g_launches.load(); }
+int64_t xcape_cuda_columns_redone(void) { return g_redone.load(); }
 int xcape_cuda_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return -1; }
@@ -685,19 +740,96 @@ int xcape_cuda_cape(const void* p, const void* t, const void* td, const void* ps
                        start_3d, cape, cin, mulev, zmulev, status, n_iter, precision, (cudaStream_t)stream);
 
   const size_t es = esize(dtype);
-  std::vector<HostIn3> in3 = {{t}, {td}};
-  if (!p_is_1d) in3.push_back({p});
-  std::vector<HostIn1> in1 = {{ps, es}, {ts, es}, {tds, es}};
-  if (start_3d) in1.push_back({start_3d, 4});
-  std::vector<HostOut> outs = {{cape, 4, 0}, {cin, 4, 0}, {mulev, 4, 0}, {zmulev, 4, 0}, {status, 4, 0}, {n_iter, 4, 0}};
-  return run_staged(ncol, nlev, base_layout(layout), es, p_is_1d ? p : nullptr, in3, in1, outs,
-                    [&](Block& b, int64_t n, cudaStream_t s) {
-                      return cape_device(p_is_1d ? b.p1d : b.in3[2], b.in3[0], b.in3[1], b.in1[0], b.in1[1], b.in1[2], n, nlev,
-                                         p_is_1d, dtype, layout, n, source, adiabat, ml_depth, pinc,
-                                         start_3d ? (const int32_t*)b.in1[3] : nullptr, (float*)b.out[0], (float*)b.out[1],
-                                         (int32_t*)b.out[2], (float*)b.out[3], status ? (int32_t*)b.out[4] : nullptr,
-                                         n_iter ? (int32_t*)b.out[5] : nullptr, precision, s);
-                    });
+  const int lay = base_layout(layout);
+  const bool rev = top_first(layout);
+  auto host_call = [&](const void* p_, const void* t_, const void* td_, const void* ps_, const void* ts_, const void* tds_,
+                       const int32_t* st3_, int64_t n, int lay_flags, int l0, int nl, float* cape_, float* cin_, int32_t* mulev_,
+                       float* zmulev_, int32_t* status_, int32_t* n_iter_) -> int {
+    std::vector<HostIn3> in3 = {{t_}, {td_}};
+    if (!p_is_1d) in3.push_back({p_});
+    std::vector<HostIn1> in1 = {{ps_, es}, {ts_, es}, {tds_, es}};
+    if (st3_) in1.push_back({st3_, 4});
+    std::vector<HostOut> outs = {{cape_, 4, 0}, {cin_, 4, 0}, {mulev_, 4, 0}, {zmulev_, 4, 0}, {status_, 4, 0}, {n_iter_, 4, 0}};
+    const bool more = nl < nlev;
+    return run_staged(n, nlev, base_layout(lay_flags), es, p_is_1d ? p_ : nullptr, in3, in1, outs,
+                      [&](Block& b, int64_t m, cudaStream_t s) {
+                        return cape_device(p_is_1d ? b.p1d : b.in3[2], b.in3[0], b.in3[1], b.in1[0], b.in1[1], b.in1[2], m, nl,
+                                           p_is_1d, dtype, lay_flags, m, source, adiabat, ml_depth, pinc,
+                                           st3_ ? (const int32_t*)b.in1[3] : nullptr, (float*)b.out[0], (float*)b.out[1],
+                                           (int32_t*)b.out[2], (float*)b.out[3], status_ ? (int32_t*)b.out[4] : nullptr,
+                                           n_iter_ ? (int32_t*)b.out[5] : nullptr, precision, s, more);
+                      }, l0, nl);
+  };
+
+  // Ship only the levels the ascent can reach.  The parcel stops at the first level with p <= 100 hPa where it is
+  // negatively buoyant (f90:554-557), which for almost every column is the 100 hPa level itself — the 10 ERA5 levels
+  // above it (27 % of the bytes) are never read.  On a shared pressure axis that level is known before anything is
+  // copied: levels up to and including the first one with p <= 100 hPa go to the device, a column that is still
+  // ascending there comes back with status 4 and is redone below with every level.
+  // Only level-major fields: they lose whole rows, which is free.  Level-last (reference-layout) fields would need a
+  // 2-D copy of ~100-byte rows, which the copy engines do at a tenth of their bandwidth (measured: 135 ms instead of 13
+  // per ERA5 field), and compacting them column by column in the pageable staging copy costs more host time than the
+  // bytes saved (17.6 vs 15.8 ms).
+  const bool can_window = lay == XCAPE_LEVEL_MAJOR;
+  int nl = nlev, l0 = 0;
+  if (p_is_1d && can_window && env_i64("XCAPE_B200_SHIP_ALL_LEVELS", 0, 0, 1) == 0) {
+    int need = nlev;
+    for (int k = 0; k < nlev; ++k) {               // k counts from the surface
+      const int ks = rev ? nlev - 1 - k : k;
+      const double pk = (dtype == XCAPE_F64) ? ((const double*)p)[ks] : (double)((const float*)p)[ks];
+      if (pk <= 100.0) { need = k + 1; break; }
+    }
+    if (need + 2 <= nlev) { nl = need; l0 = rev ? nlev - need : 0; }
+  }
+  if (nl == nlev)
+    return host_call(p, t, td, ps, ts, tds, start_3d, ncol, layout, 0, nlev, cape, cin, mulev, zmulev, status, n_iter);
+
+  static thread_local std::vector<int32_t> own_status;      // reused: a fresh 4 MB vector per call costs 0.3 ms of page faults
+  int32_t* stat = status;
+  if (!stat) {
+    if (own_status.size() < (size_t)ncol) own_status.resize((size_t)ncol);
+    stat = own_status.data();
+  }
+  rc = host_call(p, t, td, ps, ts, tds, start_3d, ncol, layout, l0, nl, cape, cin, mulev, zmulev, stat, n_iter);
+  if (rc) return rc;
+  std::vector<int64_t> redo;
+  {
+    int32_t seen = 0;                              // valid status words are 0..4: OR-ing them finds "any 4" at memory speed
+    for (int64_t c = 0; c < ncol; ++c) seen |= stat[c];
+    if (seen & 4)
+      for (int64_t c = 0; c < ncol; ++c)
+        if (stat[c] == 4) redo.push_back(c);
+  }
+  if (redo.empty()) return XCAPE_OK;
+  g_redone.fetch_add((int64_t)redo.size(), std::memory_order_relaxed);
+  // gather the unfinished columns (all levels, stored order) into a compact level-last batch and run it again
+  const int64_t m = (int64_t)redo.size();
+  std::vector<char> gt((size_t)m * nlev * es), gtd((size_t)m * nlev * es), gs((size_t)m * es * 3);
+  std::vector<int32_t> gst3(start_3d ? (size_t)m : 0), o_mu((size_t)m), o_st((size_t)m), o_it((size_t)m);
+  std::vector<float> o_cape((size_t)m), o_cin((size_t)m), o_z((size_t)m);
+  auto gather3 = [&](const void* src, char* dst) {
+    for (int64_t j = 0; j < m; ++j) {
+      const int64_t c = redo[(size_t)j];
+      if (lay == XCAPE_LEVEL_LAST) memcpy(dst + (size_t)j * nlev * es, (const char*)src + (size_t)c * nlev * es, (size_t)nlev * es);
+      else for (int k = 0; k < nlev; ++k) memcpy(dst + ((size_t)j * nlev + k) * es, (const char*)src + ((size_t)k * ncol + c) * es, es);
+    }
+  };
+  gather3(t, gt.data()); gather3(td, gtd.data());
+  const void* srf[3] = {ps, ts, tds};
+  for (int f = 0; f < 3; ++f)
+    for (int64_t j = 0; j < m; ++j) memcpy(gs.data() + ((size_t)f * m + j) * es, (const char*)srf[f] + (size_t)redo[(size_t)j] * es, es);
+  for (int64_t j = 0; j < m && start_3d; ++j) gst3[(size_t)j] = start_3d[redo[(size_t)j]];
+  rc = host_call(p, gt.data(), gtd.data(), gs.data(), gs.data() + (size_t)m * es, gs.data() + (size_t)2 * m * es,
+                 start_3d ? gst3.data() : nullptr, m, XCAPE_LEVEL_LAST | (rev ? XCAPE_LEVELS_TOP_FIRST : 0), 0, nlev,
+                 o_cape.data(), o_cin.data(), o_mu.data(), o_z.data(), o_st.data(), o_it.data());
+  if (rc) return rc;
+  for (int64_t j = 0; j < m; ++j) {
+    const int64_t c = redo[(size_t)j];
+    cape[c] = o_cape[(size_t)j]; cin[c] = o_cin[(size_t)j]; mulev[c] = o_mu[(size_t)j]; zmulev[c] = o_z[(size_t)j];
+    if (status) status[c] = o_st[(size_t)j];
+    if (n_iter) n_iter[c] = o_it[(size_t)j];
+  }
+  return XCAPE_OK;
 }
 
 int xcape_cuda_srh(const void* p, const void* t, const void* td, const void* u, const void* v,

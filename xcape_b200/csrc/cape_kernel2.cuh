@@ -172,6 +172,7 @@ __device__ __forceinline__ void col2_init(const CapeArgs& a, int64_t c, Col2& C)
   if (!C.live) return;
   if (!(a.ts[c] > 0.0f)) { C.st = 1; return; }      // model_lev.f90:77,83-88 (degC gate): zeros, MUlvl 0
   int ks = a.start ? a.start[c] : 1;                // pressure_lev.f90:154-160
+  if ((ks < 1 || ks > a.nlev) && a.more_levels) { C.st = 4; return; }   // start level outside the shipped part: needs the full column
   ks = ks < 1 ? 1 : (ks > a.nlev ? a.nlev : ks);
   C.ks = ks; C.nk = a.nlev - ks + 2;
   const Parcel P = select_source<M, SOURCE, P1D>(a, c, ks, C.nk);
@@ -180,6 +181,7 @@ __device__ __forceinline__ void col2_init(const CapeArgs& a, int64_t c, Col2& C)
   C.prev_p = P.prev.p; C.prev_pi = P.prev.pi; C.prev_thv = P.prev.thv;
   C.lev_next = ks + C.k - 2;
   C.active = C.k < C.nk;
+  if (!C.active && a.more_levels) C.st = 4;         // the parcel starts on the last level shipped: the column is taller
 }
 
 // f90:403-415 — the layer's environment, sub-step count, and the per-layer windows
@@ -261,7 +263,7 @@ __device__ __forceinline__ void col2_sub_end(Col2& C, int i) {
 }
 
 // f90:501-558 — buoyancy, trapezoid CAPE / CIN with zero-crossing split, stop rule
-__device__ __forceinline__ void col2_layer_end(Col2& C, const Layer2& Y) {
+__device__ __forceinline__ void col2_layer_end(Col2& C, const Layer2& Y, bool more_levels) {
   const float thv2 = C.th2 * (1.0f + cc::reps * C.qv2) / (1.0f + C.qv2 + C.ql2 + C.qi2);
   const float b1 = Y.b1;
   const float b2 = cc::g * (thv2 - Y.cur_thv) / Y.cur_thv;
@@ -290,7 +292,8 @@ __device__ __forceinline__ void col2_layer_end(Col2& C, const Layer2& Y) {
   C.zout = C.z;
   C.prev_p = Y.cur_p; C.prev_pi = Y.cur_pi; C.prev_thv = Y.cur_thv;
   C.lev_next = C.lev_next + 1;
-  if ((Y.cur_p <= 10000.0f && b2 < 0.0f) || !(C.k < C.nk)) C.active = false;
+  if (Y.cur_p <= 10000.0f && b2 < 0.0f) C.active = false;         // f90:554-557
+  else if (!(C.k < C.nk)) { C.active = false; if (more_levels) C.st = 4; }   // ran out of (shipped) levels while ascending
 }
 
 __device__ __forceinline__ void col2_store(const CapeArgs& a, const Col2& C) {
@@ -410,8 +413,8 @@ __global__ void __launch_bounds__(XC_CAPE2_THREADS, XC_CAPE2_MIN_BLOCKS) cape_ke
       if (doA) col2_sub_end<PSEUDO>(A, iA);
       if (doB) col2_sub_end<PSEUDO>(B, iB);
     }
-    if (YA.in && A.st == 0) col2_layer_end(A, YA);
-    if (YB.in && B.st == 0) col2_layer_end(B, YB);
+    if (YA.in && A.st == 0) col2_layer_end(A, YA, a.more_levels != 0);
+    if (YB.in && B.st == 0) col2_layer_end(B, YB, a.more_levels != 0);
   }
   col2_store(a, A);
   col2_store(a, B);

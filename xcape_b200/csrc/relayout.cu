@@ -6,6 +6,7 @@
 //   * reverse_copy: flips a shared 1-D pressure axis stored top-first (XCAPE_LEVELS_TOP_FIRST);
 //   * pres_lev_pos: core.py:286-289 (numpy masked argmin) evaluated in the input dtype.
 #include "xc_common.cuh"
+#include <atomic>
 #include "relayout.cuh"
 
 namespace xc {
@@ -81,7 +82,7 @@ __global__ void reverse_copy_kernel(const T* __restrict__ in, T* __restrict__ ou
 
 template <class T>
 __global__ void __launch_bounds__(256) pres_lev_pos_kernel(const T* __restrict__ p, const T* __restrict__ ps,
-                                                           int64_t ncol, int nlev, int32_t* __restrict__ start) {
+                                                           int64_t ncol, int nlev, int32_t* __restrict__ start, int none_value) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncol) return;
   const T s = ps[c];
@@ -94,7 +95,27 @@ __global__ void __launch_bounds__(256) pres_lev_pos_kernel(const T* __restrict__
       if (!have || d < bestd) { have = true; bestd = d; best = k; }   // argmin, first minimum
     }
   }
-  start[c] = best + 1;                     // Fortran convention                  (core.py:289)
+  // every level masked: argmin of an all-masked array is 0 -> level 1.  When only the lower part of
+  // the column was shipped (api.cu), "no level found" is not known yet: none_value = 0 makes the CAPE kernel hand the
+  // column back for a second pass with all levels
+  start[c] = have ? best + 1 : none_value; // Fortran convention                  (core.py:289)
+}
+
+// Dynamic shared memory above the 48 KB default has to be allowed per function AND per device.  The attribute is
+// set to the maximum this file ever asks for (200 KB), once per (function, device): setting the exact size on every
+// launch would let two host threads with different nlev interleave set(A), set(B < A), launch(A) -> launch failure.
+constexpr int kMaxRelayoutSmem = 200 * 1024;
+template <class K>
+cudaError_t allow_big_smem(K kernel) {
+  static std::atomic<uint64_t> done{0};           // one bit per device ordinal (per template instantiation)
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const uint64_t bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxRelayoutSmem);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
 }
 
 static inline unsigned grid_for(int64_t n, int threads, int64_t cap = 148 * 32) {
@@ -110,10 +131,10 @@ int launch_transpose_cast(const void* in, int dtype, float* out, int64_t ncol, i
   const size_t smem = (size_t)kTC * (nlev | 1) * sizeof(float);
   if (smem > 200 * 1024) return fail(XCAPE_ERR_ARG, "nlev too large for the relayout kernel (max ~790 levels)");
   if (dtype == XCAPE_F64) {
-    XC_CUDA(cudaFuncSetAttribute(transpose_cast_kernel<double, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    XC_CUDA(allow_big_smem(transpose_cast_kernel<double, float>));
     transpose_cast_kernel<double, float><<<grid, 256, smem, s>>>((const double*)in, out, ncol, nlev, ld);
   } else {
-    XC_CUDA(cudaFuncSetAttribute(transpose_cast_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    XC_CUDA(allow_big_smem(transpose_cast_kernel<float, float>));
     transpose_cast_kernel<float, float><<<grid, 256, smem, s>>>((const float*)in, out, ncol, nlev, ld);
   }
   XC_LAUNCH_CHECK();
@@ -126,10 +147,10 @@ int launch_transpose_same(const void* in, int dtype, void* out, int64_t ncol, in
   const size_t smem = (size_t)kTC * (nlev | 1) * esize(dtype);
   if (smem > 200 * 1024) return fail(XCAPE_ERR_ARG, "nlev too large for the relayout kernel");
   if (dtype == XCAPE_F64) {
-    XC_CUDA(cudaFuncSetAttribute(transpose_cast_kernel<double, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    XC_CUDA(allow_big_smem(transpose_cast_kernel<double, double>));
     transpose_cast_kernel<double, double><<<grid, 256, smem, s>>>((const double*)in, (double*)out, ncol, nlev, ld);
   } else {
-    XC_CUDA(cudaFuncSetAttribute(transpose_cast_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    XC_CUDA(allow_big_smem(transpose_cast_kernel<float, float>));
     transpose_cast_kernel<float, float><<<grid, 256, smem, s>>>((const float*)in, (float*)out, ncol, nlev, ld);
   }
   XC_LAUNCH_CHECK();
@@ -152,11 +173,11 @@ int launch_reverse_copy(const void* in, int dtype, void* out, int n, cudaStream_
   return XCAPE_OK;
 }
 
-int launch_pres_lev_pos(const void* p, const void* ps, int dtype, int64_t ncol, int nlev, int32_t* start, cudaStream_t s) {
+int launch_pres_lev_pos(const void* p, const void* ps, int dtype, int64_t ncol, int nlev, int32_t* start, cudaStream_t s, int none_value) {
   if (ncol <= 0) return XCAPE_OK;
   const unsigned blocks = (unsigned)((ncol + 255) / 256);
-  if (dtype == XCAPE_F64) pres_lev_pos_kernel<double><<<blocks, 256, 0, s>>>((const double*)p, (const double*)ps, ncol, nlev, start);
-  else pres_lev_pos_kernel<float><<<blocks, 256, 0, s>>>((const float*)p, (const float*)ps, ncol, nlev, start);
+  if (dtype == XCAPE_F64) pres_lev_pos_kernel<double><<<blocks, 256, 0, s>>>((const double*)p, (const double*)ps, ncol, nlev, start, none_value);
+  else pres_lev_pos_kernel<float><<<blocks, 256, 0, s>>>((const float*)p, (const float*)ps, ncol, nlev, start, none_value);
   XC_LAUNCH_CHECK();
   return XCAPE_OK;
 }

@@ -13,5 +13,5 @@ int launch_cast_copy(const void* in, int dtype, float* out, int64_t n, cudaStrea
 // out[i] = in[n-1-i], dtype preserved (n = nlev: one small CTA)
 int launch_reverse_copy(const void* in, int dtype, void* out, int n, cudaStream_t s);
 // core.py:286-289
-int launch_pres_lev_pos(const void* p, const void* ps, int dtype, int64_t ncol, int nlev, int32_t* start, cudaStream_t s);
+int launch_pres_lev_pos(const void* p, const void* ps, int dtype, int64_t ncol, int nlev, int32_t* start, cudaStream_t s, int none_value = 1);
 }  // namespace xc

@@ -63,7 +63,7 @@ def bind_host_to_gpu(device):
         with open(f'/sys/bus/pci/devices/{bdf}/numa_node') as f:
             node = int(f.read().strip())
         if node < 0:
-            return None
+            raise OSError('no NUMA node in sysfs')
         with open(f'/sys/devices/system/node/node{node}/cpulist') as f:
             cpus = parse_cpulist(f.read())
         allowed = os.sched_getaffinity(0)
@@ -73,7 +73,53 @@ def bind_host_to_gpu(device):
         os.sched_setaffinity(0, cpus)
         return node
     except (OSError, AttributeError, ValueError, RuntimeError, ImportError):
+        pass
+    # containers often hide the NUMA node in sysfs; the driver still knows each GPU's CPU affinity
+    try:
+        cpus = gpu_cpu_affinity(device)
+        allowed = os.sched_getaffinity(0)
+        if cpus is None or not (cpus & allowed) or (cpus & allowed) == allowed:
+            return None
+        os.sched_setaffinity(0, cpus & allowed)
+        return 'cpus ' + format_cpulist(cpus & allowed)
+    except (OSError, AttributeError, ValueError):
         return None
+
+
+def gpu_cpu_affinity(device, topo_text=None):
+    """CPU set next to GPU ``device`` from the "CPU Affinity" column of ``nvidia-smi topo -m`` (None if unavailable)."""
+    import re
+    import subprocess
+    if topo_text is None:
+        try:
+            topo_text = subprocess.run(['nvidia-smi', 'topo', '-m'], capture_output=True, text=True, timeout=20).stdout
+        except (OSError, subprocess.SubprocessError):
+            return None
+    topo_text = re.sub(r'\x1b\[[0-9;]*m', '', topo_text)
+    header = None
+    for line in topo_text.splitlines():
+        cells = [c.strip() for c in line.split('\t')]
+        if header is None and 'CPU Affinity' in cells:
+            header = cells
+            continue
+        if header is not None and cells and cells[0] == f'GPU{device}':
+            # data rows carry the row label in column 0; the header row starts with an empty cell
+            idx = header.index('CPU Affinity')
+            if idx < len(cells) and re.fullmatch(r'[0-9,\- ]+', cells[idx] or 'x'):
+                return parse_cpulist(cells[idx])
+    return None
+
+
+def format_cpulist(cpus):
+    cpus = sorted(cpus)
+    out, i = [], 0
+    while i < len(cpus):
+        j = i
+        while j + 1 < len(cpus) and cpus[j + 1] == cpus[j] + 1:
+            j += 1
+        out.append(str(cpus[i]) if i == j else f'{cpus[i]}-{cpus[j]}')
+        i = j + 1
+    return ','.join(out)
 
 
 def parse_cpulist(text):

@@ -74,6 +74,7 @@ def srh_fused(p_2d, t_2d, td_2d, u_2d, v_2d, p_s, t_s, td_s, u_s, v_s, flag_1d, 
     lm = A.empty_like_host_or_device(ref, (ngrid, 2), 'float32') if want_all else None
     m6 = A.empty_like_host_or_device(ref, (ngrid, 2), 'float32') if want_all else None
     es = 4 if dt == _lib.F32 else 8
+    A.order_on_stream(ref, stream, [p, t_, td_, u_, v_, ps_, ts_, tds_, us_, vs_, start, srm, slm, rm, lm, m6])
 
     def call(c0, c1, dev):
         n = c1 - c0
@@ -142,6 +143,7 @@ def srh(u_2d, v_2d, aglh_2d, u_s, v_s, aglh_s, pres_lev_pos, depth, type_grid, o
     rm = A.empty_like_host_or_device(ref, (ngrid, 2), 'float32') if want_all else None
     lm = A.empty_like_host_or_device(ref, (ngrid, 2), 'float32') if want_all else None
     m6 = A.empty_like_host_or_device(ref, (ngrid, 2), 'float32') if want_all else None
+    A.order_on_stream(ref, stream, [u_, v_, h_, us_, vs_, hs_, start, srm, slm, rm, lm, m6])
     rc = L.xcape_cuda_srh_from_heights(A.ptr(u_), A.ptr(v_), A.ptr(h_), A.ptr(us_), A.ptr(vs_), A.ptr(hs_),
                                        C.c_int64(ngrid), nlev, dt, layout | (_lib.LEVELS_TOP_FIRST if top_first else 0), mem,
                                        C.c_double(float(depth)), A.ptr(start),

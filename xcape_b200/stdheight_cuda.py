@@ -44,6 +44,7 @@ def stdheight(p_2d, t_2d, td_2d, p_s, t_s, td_s, flag_1d, pres_lev_pos, aglh0, t
         h = A.empty_like_host_or_device(ref, (ngrid, nlev), 'float64')
         h_view = h.t() if A.is_cuda(ref) else h.T
     hs = A.empty_like_host_or_device(ref, (ngrid,), 'float64')
+    A.order_on_stream(ref, stream, [p, t_, td_, ps_, ts_, tds_, start, h, hs])
     rc = L.xcape_cuda_stdheight(A.ptr(p), A.ptr(t_), A.ptr(td_), A.ptr(ps_), A.ptr(ts_), A.ptr(tds_),
                                 C.c_int64(ngrid), nlev, p_is_1d, dt, layout | (_lib.LEVELS_TOP_FIRST if top_first else 0), mem,
                                 C.c_double(float(aglh0)),

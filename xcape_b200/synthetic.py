@@ -45,7 +45,7 @@ def _smooth01(ci, grid, k1, k2, ph, noise):
     return np.clip(f, 0.0, 1.0)
 
 
-def _block(seed, b, grid, nlev, vertical_lev, active, ncol_total, perm):
+def _block(seed, b, grid, nlev, vertical_lev, active, ncol_total, perm, winds=True):
     c0 = b * BLOCK
     n = min(BLOCK, ncol_total - c0)
     g = np.random.Generator(np.random.Philox(key=int(seed), counter=[0, 0, 0, int(b)]))
@@ -70,15 +70,16 @@ def _block(seed, b, grid, nlev, vertical_lev, active, ncol_total, perm):
     else:
         p = ps[:, None] * sigma_levels(nlev)[None, :] * 0.997
     zkm = 44.3308 * (1.0 - (p / ps[:, None]) ** 0.190263)
-    nz = g.standard_normal((4, n, nlev))
+    # the stream is consumed in order, so drawing only the first two planes gives the same t / td as drawing all four
+    nz = g.standard_normal((4 if winds else 2, n, nlev))
     t = np.maximum(ts[:, None] - lapse[:, None] * zkm, ttrop[:, None]) + 0.3 * nz[0]
     td = t - (dep[:, None] + dgrad[:, None] * np.maximum(zkm, 0.0) + np.abs(nz[1]))
-    u = 5.0 + 3.0 * zkm + 2.0 * nz[2]
-    v = 2.0 + 15.0 * np.sin(zkm / 3.0) + 2.0 * nz[3]
-    us, vs = 0.7 * u[:, 0], 0.7 * v[:, 0]
     f = np.float32
-    out = dict(t=t.astype(f), td=td.astype(f), u=u.astype(f), v=v.astype(f), ps=ps.astype(f), ts=ts.astype(f),
-               tds=tds.astype(f), us=us.astype(f), vs=vs.astype(f))
+    out = dict(t=t.astype(f), td=td.astype(f), ps=ps.astype(f), ts=ts.astype(f), tds=tds.astype(f))
+    if winds:
+        u = 5.0 + 3.0 * zkm + 2.0 * nz[2]
+        v = 2.0 + 15.0 * np.sin(zkm / 3.0) + 2.0 * nz[3]
+        out.update(u=u.astype(f), v=v.astype(f), us=(0.7 * u[:, 0]).astype(f), vs=(0.7 * v[:, 0]).astype(f))
     if vertical_lev != 'pressure':
         out['p'] = p.astype(f)
     return out
@@ -110,16 +111,20 @@ def make_soundings(config='C2', cols=None, active=True, shuffle=False, grid=None
     perm = None
     if shuffle:
         perm = np.random.Generator(np.random.Philox(key=cfg['seed'] + 7919)).permutation(ntot)
-    parts = []
-    for b in range(c0 // BLOCK, (max(c1, c0 + 1) - 1) // BLOCK + 1):
-        blk = _block(cfg['seed'], b, cfg['grid'], cfg['nlev'], cfg['vertical_lev'], active, ntot, perm)
+    def part(b):
+        blk = _block(cfg['seed'], b, cfg['grid'], cfg['nlev'], cfg['vertical_lev'], active, ntot, perm, winds)
         lo, hi = max(c0 - b * BLOCK, 0), min(c1 - b * BLOCK, BLOCK)
-        parts.append({k: a[lo:hi] for k, a in blk.items()})
+        return {k: a[lo:hi] for k, a in blk.items()}
+    blocks = range(c0 // BLOCK, (max(c1, c0 + 1) - 1) // BLOCK + 1)
+    if len(blocks) >= 8:                      # blocks are independent: numpy releases the GIL in the heavy calls
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(min(16, len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else 4)) as ex:
+            parts = list(ex.map(part, blocks))
+    else:
+        parts = [part(b) for b in blocks]
     keys = parts[0].keys()
     out = {k: np.concatenate([q[k] for q in parts], axis=0) for k in keys}
-    if not winds:
-        for k in ('u', 'v', 'us', 'vs'):
-            out.pop(k)
     if cfg['vertical_lev'] == 'pressure':
         out['p'] = ERA5_LEVELS_HPA[:cfg['nlev']].copy()
     out.update(vertical_lev=cfg['vertical_lev'], grid=cfg['grid'], cols=(c0, c1))

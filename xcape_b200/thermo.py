@@ -44,6 +44,7 @@ def dewpoint_from_q(p, q, *, lev_axis=-1, q_min=1e-10, device=0, stream=None):
     ncol = int(np.prod(q.shape)) // max(nlev, 1)
     layout = _lib.LEVEL_MAJOR if (lev_axis == 0 and q.ndim > 1) else _lib.LEVEL_LAST
     out = A.empty_like_host_or_device(q_, tuple(q.shape), dt)
+    A.order_on_stream(q_, stream, [p_, q_, out])
     rc = L.xcape_cuda_dewpoint_from_q(A.ptr(p_), A.ptr(q_), C.c_int64(ncol), int(nlev), p_is_1d,
                                       _lib.F32 if dt == 'float32' else _lib.F64, layout,
                                       _lib.MEM_DEVICE if all(on_dev) else _lib.MEM_HOST, C.c_double(float(q_min)),
