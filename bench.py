@@ -667,6 +667,12 @@ def main():
         if os.path.exists(peaks_file):
             hbm_peak, hbm_src = float(json.load(open(peaks_file))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
         roofline = wl.roofline(ms_kernel, st, fp32_peak, fp64_peak, hbm_peak, hbm_src)
+        if wl.kind == 'cape':
+            rrr = _lib.measure_fp32_rrr(local_rank, 5)
+            roofline['fp32_peak_three_register_operands'] = {
+                'peak': rrr, 'frac': roofline['achieved'] / rrr,
+                'what': 'FFMA with three distinct register operands and no reuse (xcape_cuda_measure_fp32_rrr): the rate the '
+                        'register file sustains for real code; `peak` above feeds two operands from uniform registers'}
         if variants:
             for v in variants.values():
                 v['frac_of_fp32_peak'] = FLOP_PER_ITER * v['reference_iterations_per_column'] * ncol / (v['kernel_ms'] * 1e-3) / 1e12 / fp32_peak

@@ -173,6 +173,9 @@ XCAPE_API int xcape_cuda_dewpoint_from_q(const void* p, const void* q, int64_t n
 /* Measured arithmetic peaks of `device` (roofline denominators the driver's MEASURED_PEAKS.json
  * lacks): dependent-chain-free FFMA / DFMA loops, 2 flop per FMA, best of `reps` launches. */
 XCAPE_API int xcape_cuda_measure_peaks(int device, int reps, double* fp32_tflops, double* fp64_tflops);
+/* FFMA rate with three distinct register operands per instruction (no uniform / immediate operands, no reuse): the
+ * rate the register file lets a real kernel sustain — ~0.70 of the figure above on B200.  Reported beside it. */
+XCAPE_API int xcape_cuda_measure_fp32_rrr(int device, int reps, double* fp32_tflops);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_NODEV = 0, 1, 2, 3
 SYMBOLS = ('xcape_cuda_cape', 'xcape_cuda_srh', 'xcape_cuda_srh_from_heights', 'xcape_cuda_stdheight', 'xcape_cuda_pres_lev_pos',
            'xcape_cuda_last_error', 'xcape_cuda_device_count', 'xcape_cuda_version',
            'xcape_cuda_kernel_launches', 'xcape_cuda_measure_peaks', 'xcape_cuda_release_memory',
-           'xcape_cuda_dewpoint_from_q', 'xcape_cuda_columns_redone')
+           'xcape_cuda_dewpoint_from_q', 'xcape_cuda_columns_redone', 'xcape_cuda_measure_fp32_rrr')
 
 _lib = None
 
@@ -70,6 +70,8 @@ def lib():
         L.xcape_cuda_release_memory.argtypes = [i32]
         L.xcape_cuda_measure_peaks.restype = i32
         L.xcape_cuda_measure_peaks.argtypes = [i32, i32, C.POINTER(f64), C.POINTER(f64)]
+        L.xcape_cuda_measure_fp32_rrr.restype = i32
+        L.xcape_cuda_measure_fp32_rrr.argtypes = [i32, i32, C.POINTER(f64)]
         _lib = L
     return _lib
 
@@ -96,6 +98,13 @@ def measure_peaks(device=0, reps=5):
     a, b = C.c_double(0.0), C.c_double(0.0)
     check(lib().xcape_cuda_measure_peaks(int(device), int(reps), C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def measure_fp32_rrr(device=0, reps=5):
+    """FFMA TFLOP/s with three distinct register operands per instruction (what the register file sustains)."""
+    a = C.c_double(0.0)
+    check(lib().xcape_cuda_measure_fp32_rrr(int(device), int(reps), C.byref(a)))
+    return a.value
 
 
 def release_memory(device=0):

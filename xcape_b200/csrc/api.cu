@@ -704,6 +704,13 @@ int xcape_cuda_measure_peaks(int device, int reps, double* fp32_tflops, double* 
   return measure_peaks(reps, fp32_tflops, fp64_tflops);
 }
 
+int xcape_cuda_measure_fp32_rrr(int device, int reps, double* fp32_tflops) {
+  if (!fp32_tflops) return fail(XCAPE_ERR_ARG, "null pointer");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(XCAPE_ERR_NODEV, "cudaSetDevice failed");
+  return measure_fp32_rrr(reps, fp32_tflops);
+}
+
 int xcape_cuda_pres_lev_pos(const void* p, const void* ps, int64_t ncol, int nlev, int dtype, int mem,
                             int32_t* start_3d, int device, void* stream) {
   int rc = check_common(ncol, nlev, dtype, XCAPE_LEVEL_LAST, mem);

@@ -2,4 +2,5 @@
 #pragma once
 namespace xc {
 int measure_peaks(int reps, double* fp32_tflops, double* fp64_tflops);
+int measure_fp32_rrr(int reps, double* tflops);
 }
