@@ -673,6 +673,13 @@ def main():
                 'peak': rrr, 'frac': roofline['achieved'] / rrr,
                 'what': 'FFMA with three distinct register operands and no reuse (xcape_cuda_measure_fp32_rrr): the rate the '
                         'register file sustains for real code; `peak` above feeds two operands from uniform registers'}
+        if other is not None and 'total_iter' in st:
+            tf_o = FLOP_PER_ITER * st['total_iter'] / (other['kernel_ms'] * 1e-3) / 1e12
+            other['roofline'] = {'bound': 'fp32', 'achieved': tf_o, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': tf_o / fp32_peak,
+                                 'work': 'reference-algorithm iterations (the fast solve executes about a third of them)'}
+            other['value'] = world * ncol / (other['device_path_ms_per_step'] * 1e-3)
+            other['parity'] = ('tolerance-level: every well-conditioned column inside max(1 J/kg, 1e-4 rel) for CAPE and CIN, MU level and '
+                               'convergence status identical (tests/test_gpu_parity.py::test_fast_mode_full_era5_field)')
         if variants:
             for v in variants.values():
                 v['frac_of_fp32_peak'] = FLOP_PER_ITER * v['reference_iterations_per_column'] * ncol / (v['kernel_ms'] * 1e-3) / 1e12 / fp32_peak

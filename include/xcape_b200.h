@@ -63,10 +63,15 @@ enum { XCAPE_FAITHFUL = 0,
        XCAPE_FAST = 1,
 /* XCAPE_FAST additionally replaces the reference's damped fixed-point iteration of a sub-step
  * (x += 0.3 g, ~10 passes) by a safeguarded secant solve of the same equation with the same stopping
- * rule (3-5 passes) and advances the Exner function incrementally between level anchors.
- * XCAPE_FAST_RELAXED keeps the reference's iteration (identical pass counts and non-convergence
- * behaviour) and only uses the fast arithmetic. */
-       XCAPE_FAST_RELAXED = 2 };
+ * rule (3-5 passes) and advances the Exner function incrementally between level anchors.  Sub-steps on
+ * which the reference's own iteration cannot converge (slope of the map below ~-6: limit cycle, status 2,
+ * cape = cin = 0) are detected from the secant slope and decided by the reference's
+ * iteration, so the non-convergence semantics are the reference's.
+ * XCAPE_FAST_RELAXED keeps the reference's iteration everywhere (identical pass counts) and only uses the
+ * fast arithmetic.  XCAPE_FAST_OPTIMISTIC is XCAPE_FAST without that detection: where the reference gives
+ * up, the converged secant value is returned with status 0. */
+       XCAPE_FAST_RELAXED = 2,
+       XCAPE_FAST_OPTIMISTIC = 3 };
 /* per-column status word (optional output) */
 enum { XCAPE_ST_OK = 0, XCAPE_ST_SKIPPED = 1 /* ts <= 0 degC gate, f90:77 */,
        XCAPE_ST_NONCONVERGED = 2 /* > 100 moist iterations, f90:464-474: cape = cin = 0 */,

@@ -87,14 +87,17 @@ def loopcape_ml(p3d, t3d, td3d, ps, ts, tds, pinc, source, ml_depth, adiabat,
     cape = np.zeros(n2, np.float32); cin = np.zeros(n2, np.float32)
     mulvl = np.zeros(n2, np.int32); zout = np.zeros(n2, np.float32)
     cnt = [np.zeros(n2, np.int32) for _ in range(3)] if counters else [None] * 3
+    cond = np.full(n2, np.inf, np.float32) if counters else None
+    lib(contract).xcape_ref_set_cond_buffer(_p(cond))
     rc = lib(contract).xcape_ref_loopcape_ml(
         _p(p3d), _p(t3d), _p(td3d), _p(ps), _p(ts), _p(tds), C.c_float(pinc), C.c_int(source),
         C.c_float(ml_depth), C.c_int(adiabat), C.c_int(nk), C.c_int64(n2), _p(cape), _p(cin),
         _p(mulvl), _p(zout), C.c_int(tmode), C.c_int(nthreads), _p(cnt[0]), _p(cnt[1]), _p(cnt[2]))
+    lib(contract).xcape_ref_set_cond_buffer(None)
     if rc:
         raise ValueError('oracle: bad source/adiabat/pinc')
     if counters:
-        return cape, cin, mulvl, zout, dict(n_iter=cnt[0], n_sub=cnt[1], status=cnt[2])
+        return cape, cin, mulvl, zout, dict(n_iter=cnt[0], n_sub=cnt[1], status=cnt[2], cond_b=cond)
     return cape, cin, mulvl, zout
 
 
@@ -110,15 +113,18 @@ def loopcape_pl1d(t3d, td3d, p, ps, ts, tds, pinc, source, ml_depth, adiabat, st
     cape = np.zeros(n2, np.float32); cin = np.zeros(n2, np.float32)
     mulvl = np.zeros(n2, np.int32); zout = np.zeros(n2, np.float32)
     cnt = [np.zeros(n2, np.int32) for _ in range(3)] if counters else [None] * 3
+    cond = np.full(n2, np.inf, np.float32) if counters else None
+    lib(contract).xcape_ref_set_cond_buffer(_p(cond))
     rc = lib(contract).xcape_ref_loopcape_pl1d(
         _p(t3d), _p(td3d), _p(p), _p(ps), _p(ts), _p(tds), C.c_float(pinc), C.c_int(source),
         C.c_float(ml_depth), C.c_int(adiabat), _p(start), C.c_int(nk), C.c_int64(n2), _p(cape),
         _p(cin), _p(mulvl), _p(zout), C.c_int(tmode), C.c_int(nthreads), _p(cnt[0]), _p(cnt[1]),
         _p(cnt[2]))
+    lib(contract).xcape_ref_set_cond_buffer(None)
     if rc:
         raise ValueError('oracle: bad source/adiabat/pinc')
     if counters:
-        return cape, cin, mulvl, zout, dict(n_iter=cnt[0], n_sub=cnt[1], status=cnt[2])
+        return cape, cin, mulvl, zout, dict(n_iter=cnt[0], n_sub=cnt[1], status=cnt[2], cond_b=cond)
     return cape, cin, mulvl, zout
 
 

@@ -382,7 +382,15 @@ template <int TM> inline float getthe(float p, float t, float td, float q) {   /
          t_exp<TM>(((3376.0f / tlcl) - 2.54f) * q * (1.0f + 0.81f * q));
 }
 
-struct ColOut { float cape, cin, zout; int32_t mulvl; int32_t n_iter, n_sub, status; };
+struct ColOut { float cape, cin, zout; int32_t mulvl; int32_t n_iter, n_sub, status; float cond_b; };
+
+// Conditioning word (SURVEY §8d "ill-conditioned columns"): CIN is only credited when positive area is (re)entered
+// (f90:509-523), so at a level where the parcel arrives with b1 < 0 the SIGN of b2 decides between "credit the
+// negative area accumulated so far" and "keep accumulating" — the one place where CAPE/CIN are discontinuous in the
+// buoyancy.  cond_b = min over such levels of |b2| (m/s2; +inf if there is none): a column whose cond_b is far above
+// the arithmetic noise of an implementation cannot flip, one near zero can.  Written to the buffer registered with
+// xcape_ref_set_cond_buffer (tests of the tolerance-level `fast` modes classify columns with it).
+float* g_cond_out = nullptr;
 
 // Diagnostic trace (profiles/divergence_model.py): per column, a list of int16 — for every layer of the ascent
 // -(1000 + k), -nloop, then the number of moist passes of each of its sub-steps.  Used to model what a SIMT warp pays for
@@ -434,7 +442,7 @@ void getcape(const float* pA, const float* tA, const float* tdA, int64_t ls_p, i
   o.mulvl = -999999;                                            // f90:252-253
   o.zout = -999999.0f;
   o.cape = 0.0f; o.cin = 0.0f;
-  o.n_iter = 0; o.n_sub = 0; o.status = ST_OK;
+  o.n_iter = 0; o.n_sub = 0; o.status = ST_OK; o.cond_b = INFINITY;
 
   int kmax = 1;
   double avgth = 0.0, avgqv = 0.0;
@@ -557,6 +565,7 @@ void getcape(const float* pA, const float* tA, const float* tdA, int64_t ls_p, i
     }
     thv2 = th2 * (1.0f + c_reps * qv2) / (1.0f + qv2 + ql2 + qi2);   // f90:501-503
     b2 = c_g * (thv2 - thv[k]) / thv[k];
+    if (b1 < 0.0f) o.cond_b = std::min(o.cond_b, std::fabs(b2));
     float dz = -c_cpdg * 0.5f * (thv[k] + thv[k - 1]) * (pi[k] - pi[k - 1]);
     float parea;
     if (b2 >= 0.0f && b1 < 0.0f) {                               // f90:509-545
@@ -601,9 +610,10 @@ void loopcape_range(int64_t i0, int64_t i1, const float* p3d, const float* t3d, 
       getcape<TM>(pcol, t3d + i * nk + (ks - 1), td3d + i * nk + (ks - 1), 1, 1, ps[i], ts[i],
                   tds[i], pinc, source, ml_depth, adiabat, nk_used, w, o);
     } else {
-      o.cape = 0; o.cin = 0; o.zout = 0; o.mulvl = 0; o.n_iter = 0; o.n_sub = 0; o.status = ST_SKIPPED;
+      o.cape = 0; o.cin = 0; o.zout = 0; o.mulvl = 0; o.n_iter = 0; o.n_sub = 0; o.status = ST_SKIPPED; o.cond_b = INFINITY;
     }
     cape[i] = o.cape; cin[i] = o.cin; mulvl[i] = o.mulvl; zout[i] = o.zout;
+    if (g_cond_out) g_cond_out[i] = o.cond_b;
     if (n_iter) n_iter[i] = o.n_iter;
     if (n_sub) n_sub[i] = o.n_sub;
     if (status) status[i] = o.status;
@@ -760,6 +770,9 @@ int xcape_ref_loopcape_pl1d(const float* t3d, const float* td3d, const float* p1
   });
   return 0;
 }
+
+// register (or clear, with nullptr) the per-column output buffer of the conditioning word for the NEXT loopcape call
+void xcape_ref_set_cond_buffer(float* buf) { g_cond_out = buf; }
 
 // diagnostic: loopcape_pl1d / loopcape_ml (SPEC arithmetic, one thread) with the per-sub-step pass counts of every
 // column written to trace[i*cap .. ) (see g_trace above; unused slots stay 0)

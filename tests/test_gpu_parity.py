@@ -17,6 +17,7 @@ from conftest import close_decimal, era_cape_args, era_srh_args, snd_cape_args, 
 
 pytestmark = pytest.mark.gpu
 
+ILL_B = 1e-5       # m/s2: |b2| at a CIN-credit decision below which a column counts as ill-conditioned (oracle cond_b)
 SOURCES = ['surface', 'most-unstable', 'mixed-layer']
 ADIABATS = ['pseudo-liquid', 'reversible-liquid', 'pseudo-ice', 'reversible-ice']
 
@@ -536,23 +537,48 @@ def test_fast_mode_within_stated_tolerance(core, oracle_mod, cfg, vertical_lev, 
     exact = core.calc_cape(*args, method='cuda', precision='faithful', **kw)
     ref, cnt = oracle_mod.calc_cape_ref(*args, tmode=oracle_mod.LIBM, nthreads=8, counters=True, **kw)
     per = oracle_mod.calc_cape_ref(*args, tmode=oracle_mod.LIBM, nthreads=8, contract=True, **kw)
-    ill = ~(tol_ok(per[0], ref[0]) & tol_ok(per[1], ref[1])) | (cnt['status'] == 2)
+    # ill-conditioned: the oracle itself moves beyond tolerance under FMA contraction, its iteration gives
+    # up, or — the conditioning word the oracle exports — the column passes a CIN-credit decision (b1 < 0, sign of b2)
+    # with |b2| < 1e-5 m/s2, i.e. within the arithmetic noise of ANY implementation of the ascent
+    ill = ~(tol_ok(per[0], ref[0]) & tol_ok(per[1], ref[1])) | (cnt['status'] == 2) | (cnt['cond_b'] < ILL_B)
     cape_ok, cin_ok = tol_ok(fast[0], ref[0]), tol_ok(fast[1], ref[1])
     n = cape_ok.size
     print(f'{cfg} {source} {precision}: CAPE outside tol {(~cape_ok).sum()}/{n}, CIN outside tol {(~cin_ok).sum()}/{n} '
-          f'(oracle-ill-conditioned {ill.sum()}); max|dCAPE| {np.abs(fast[0] - ref[0])[~ill].max():.3f} J/kg, '
-          f'mean {np.abs(fast[0] - ref[0]).mean():.4f}')
-    # CAPE: inside the stated tolerance on every column the reference itself computes stably.
+          f'(ill-conditioned {ill.sum()}, of which cond_b < {ILL_B:g}: {(cnt["cond_b"] < ILL_B).sum()}); '
+          f'max|dCAPE| {np.abs(fast[0] - ref[0])[~ill].max():.3f} J/kg, mean {np.abs(fast[0] - ref[0]).mean():.4f}')
+    # §8d's rule: 100 % of the well-conditioned columns inside the stated tolerance, CAPE and CIN alike
     assert (~cape_ok & ~ill).sum() == 0
-    # CIN: the reference credits negative area only when positive area is (re)entered (f90:509-523), so
-    # CIN jumps by tens of J/kg when a near-zero buoyancy changes sign — typically on columns with
-    # CAPE < 1 J/kg.  Those sign flips are the only disagreements and stay below 1e-4 of the columns.
+    assert (~cin_ok & ~ill).sum() == 0
+    assert ill.mean() < 3e-3
+    # and the disagreements that remain among the ill-conditioned ones stay rare
     assert (~cin_ok).mean() < 1e-4, (~cin_ok).sum()
     if source == 'most-unstable':
         assert np.array_equal(fast[2], exact[2])                   # MU level: same prep arithmetic, bit-exact
         assert (fast[3] != exact[3]).mean() < 1e-3                 # last level reached can differ on a sign flip
     # the fast body must not be further from the reference than the faithful one by more than a fraction of the tolerance
     assert np.abs(fast[0] - ref[0])[~ill].mean() < 0.1 and np.abs(fast[0] - ref[0])[~ill].max() < 0.5
+
+
+def test_fast_mode_full_era5_field(core, oracle_mod):
+    """precision='fast' on ALL 1 038 240 columns of BASELINE configs[1] against the reference arithmetic (oracle with
+    glibc libm): every well-conditioned column inside max(1 J/kg, 1e-4 rel) for CAPE and CIN, MU level identical on
+    all columns, convergence status identical on all columns."""
+    from xcape_b200.cape_cuda import cape as cape_cuda
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C2', winds=False)
+    args = (d['p'], d['t'], d['td'], d['ps'], d['ts'], d['tds'])
+    kw = dict(source='most-unstable', adiabat='pseudo-liquid', pinc=500., vertical_lev='pressure')
+    fast = cape_cuda(d['p'], d['t'].T, d['td'].T, d['ps'], d['ts'], d['tds'], 1, None, 2, 500., 1, 500., 2, precision='fast',
+                     return_status=True)
+    ref, cnt = oracle_mod.calc_cape_ref(*args, tmode=oracle_mod.LIBM, nthreads=os.cpu_count() or 8, counters=True, **kw)
+    ill = (cnt['status'] == 2) | (cnt['cond_b'] < ILL_B)
+    cape_ok, cin_ok = tol_ok(fast[0], ref[0]), tol_ok(fast[1], ref[1])
+    print(f'full C2 fast: CAPE outside tol {(~cape_ok).sum()}, CIN outside tol {(~cin_ok).sum()} of {cape_ok.size}; '
+          f'ill-conditioned (cond_b < {ILL_B:g} m/s2 or reference non-converged): {ill.sum()}')
+    assert (~cape_ok & ~ill).sum() == 0 and (~cin_ok & ~ill).sum() == 0
+    assert ill.mean() < 3e-3 and (~cin_ok).sum() <= 30
+    assert np.array_equal(fast[2], ref[2])
+    assert np.array_equal(fast[4], cnt['status'])
 
 
 def test_fast_mode_goldens(core, soundings, era5pl):
@@ -624,13 +650,14 @@ def test_fast_mode_all_adiabats(core, oracle_mod, adiabat, source, precision):
         assert np.array_equal(fast[2], ref[2]) or (fast[2] != ref[2]).mean() < 1e-3
 
 
-@pytest.mark.parametrize('precision', ['fast', 'fast-relaxed'])
+@pytest.mark.parametrize('precision', ['fast', 'fast-relaxed', 'fast-optimistic'])
 def test_fast_mode_on_edge_columns(core, oracle_mod, precision):
     """The edge set of test_gate_nonconvergence_and_high_surface in the fast modes: gates and the
     high-surface MU rule are exact (shared prep code); outputs are finite; where the reference
     converges the tolerance holds.  Where the reference gives up after 100 passes (status 2 ->
-    cape = cin = 0) 'fast-relaxed' gives up too (same iteration); 'fast' (secant) may converge and
-    then reports the converged CAPE with status 0 — the one documented behavioural difference."""
+    cape = cin = 0) 'fast-relaxed' gives up too (same iteration) and so does 'fast', which hands every sub-step
+    whose secant slope says "the damped map cannot converge here" to the reference's iteration;
+    'fast-optimistic' (opt-in) keeps the converged secant value with status 0 instead."""
     from xcape_b200.cape_cuda import cape as cape_cuda
     from xcape_b200.synthetic import make_soundings
     d = make_soundings('C1', cols=(0, 512))
@@ -652,11 +679,13 @@ def test_fast_mode_on_edge_columns(core, oracle_mod, precision):
         conv = (cnt['status'] == 0) & (got[4] == 0)
         assert tol_ok(got[0], ref[0])[conv].all()
         assert (~tol_ok(got[1], ref[1])[conv]).sum() <= 1
-        assert ((cnt['status'] == 0) & (got[4] == 2)).sum() <= (8 if precision == 'fast-relaxed' else 0)
+        assert ((cnt['status'] == 0) & (got[4] == 2)).sum() <= (0 if precision == 'fast-optimistic' else 8)
         if source == 'most-unstable':
             assert np.array_equal(got[2], ref[2]) and (got[2][100:110] == -999999).all()
-        if precision == 'fast-relaxed':
-            assert ((got[4] == 2) == (cnt['status'] == 2)).mean() > 0.95
+        if precision != 'fast-optimistic':
+            agree = ((got[4] == 2) == (cnt['status'] == 2))
+            print(f'{source} {precision}: reference gives up on {(cnt["status"] == 2).sum()} columns, status agrees on {agree.mean():.3f}')
+            assert agree.mean() > 0.95
         else:
             gave_up = cnt['status'] == 2
             print(f'{source}: reference gives up on {gave_up.sum()} columns; secant solve converges on '

@@ -14,8 +14,8 @@ F32, F64 = 0, 1
 LEVEL_LAST, LEVEL_MAJOR = 0, 1
 LEVELS_TOP_FIRST = 0x100      # flag OR-ed into the layout: level axis stored top -> surface
 MEM_HOST, MEM_DEVICE = 0, 1
-FAITHFUL, FAST, FAST_RELAXED = 0, 1, 2
-PRECISION = {'faithful': FAITHFUL, 'fast': FAST, 'fast-relaxed': FAST_RELAXED}
+FAITHFUL, FAST, FAST_RELAXED, FAST_OPTIMISTIC = 0, 1, 2, 3
+PRECISION = {'faithful': FAITHFUL, 'fast': FAST, 'fast-relaxed': FAST_RELAXED, 'fast-optimistic': FAST_OPTIMISTIC}
 OK, ERR_ARG, ERR_CUDA, ERR_NODEV = 0, 1, 2, 3
 
 # every symbol include/xcape_b200.h declares (tests check the library exports all of them)

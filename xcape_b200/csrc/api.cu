@@ -185,7 +185,10 @@ int cape_device(const void* p, const void* t, const void* td, const void* ps, co
   a.ncol = ncol; a.ld = ld; a.nlev = nlev; a.pinc = pinc; a.ml_depth = ml_depth;
   a.cape = cape; a.cin = cin; a.zout = zmulev; a.mulvl = mulev; a.status = status; a.n_iter = n_iter;
   if (precision == XCAPE_FAITHFUL) return launch_cape_faithful(a, source, adiabat, p_is_1d != 0, s);
-  if (precision == XCAPE_FAST) return launch_cape_fast(a, source, adiabat, p_is_1d != 0, s);
+  if (precision == XCAPE_FAST || precision == XCAPE_FAST_OPTIMISTIC) {
+    a.keep_secant = (precision == XCAPE_FAST_OPTIMISTIC) ? 1 : 0;
+    return launch_cape_fast(a, source, adiabat, p_is_1d != 0, s);
+  }
   if (precision == XCAPE_FAST_RELAXED) return launch_cape_fast_relaxed(a, source, adiabat, p_is_1d != 0, s);
   return fail(XCAPE_ERR_ARG, "unknown precision mode");
 }
@@ -736,7 +739,7 @@ int xcape_cuda_cape(const void* p, const void* t, const void* td, const void* ps
   if (source < 1 || source > 3) return fail(XCAPE_ERR_ARG, "source must be 1 (surface), 2 (most-unstable) or 3 (mixed-layer)");
   if (adiabat < 1 || adiabat > 4) return fail(XCAPE_ERR_ARG, "adiabat must be 1..4");
   if (!(pinc > 0.0f)) return fail(XCAPE_ERR_ARG, "pinc must be > 0");
-  if (precision < XCAPE_FAITHFUL || precision > XCAPE_FAST_RELAXED) return fail(XCAPE_ERR_ARG, "unknown precision mode");
+  if (precision < XCAPE_FAITHFUL || precision > XCAPE_FAST_OPTIMISTIC) return fail(XCAPE_ERR_ARG, "unknown precision mode");
   if (ncol == 0) return XCAPE_OK;
   if (!p || !t || !td || !ps || !ts || !tds || !cape || !cin || !mulev || !zmulev) return fail(XCAPE_ERR_ARG, "null pointer");
   DeviceGuard dg(device);

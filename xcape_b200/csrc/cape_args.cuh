@@ -23,6 +23,7 @@ struct CapeArgs {
   int32_t* __restrict__ mulvl;
   int32_t* __restrict__ status;    // nullable
   int32_t* __restrict__ n_iter;    // nullable: moist iterations executed (roofline work counter)
+  int keep_secant;                 // fast mode only: keep the secant solve's value where the reference's iteration gives up
   int more_levels;                 // the 3-D arrays hold only the lowest `nlev` levels of a taller column (host path, see api.cu):
                                    // a column still ascending after the last one gets status 4 (internal) and is redone
   const float* __restrict__ pl_pi; // P1D only, nullable: Exner function of the nlev pressure levels, precomputed once per

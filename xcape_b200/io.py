@@ -67,6 +67,7 @@ class ZarrArray:
         self.fill_value = meta.get('fill_value')
         self.sep = meta.get('dimension_separator', '.')
         self._decode = _decompressor(meta.get('compressor'))
+        self._raw = meta.get('compressor') is None
         self.attrs = {}
         zattrs = os.path.join(path, '.zattrs')
         if os.path.exists(zattrs):
@@ -85,6 +86,31 @@ class ZarrArray:
         with open(fn, 'rb') as f:
             raw = self._decode(f.read())
         return np.frombuffer(raw, dtype=self.dtype).reshape(self.chunks, order=self.order)
+
+    def _read_into(self, cid, lo, hi, out):
+        """Fast path: an uncompressed C-order chunk that lies wholly inside the selection and lands on a contiguous
+        run of ``out`` is read from its file straight into place (no intermediate buffer, no second copy)."""
+        if self._raw is False or self.order != 'C':
+            return False
+        dst = []
+        for k, (c, l, h, n) in enumerate(zip(self.chunks, lo, hi, self.shape)):
+            c0 = cid[k] * c
+            if c0 < l or c0 + c > h:                 # chunk sticks out of the selection (or is a padded edge chunk)
+                return False
+            dst.append(slice(c0 - l, c0 - l + c))
+        view = out[tuple(dst)]
+        if not view.flags['C_CONTIGUOUS']:
+            return False
+        name = self.sep.join(str(i) for i in cid)
+        fn = os.path.join(self.path, *name.split('/')) if self.sep == '/' else os.path.join(self.path, name)
+        try:
+            with open(fn, 'rb', buffering=0) as f:
+                got = f.readinto(memoryview(view).cast('B'))
+        except FileNotFoundError:
+            return False
+        if got != view.nbytes:
+            raise IOError(f'short chunk file {fn}')
+        return True
 
     def __getitem__(self, sel):
         sel = sel if isinstance(sel, tuple) else (sel,)
@@ -109,6 +135,8 @@ class ZarrArray:
         ranges = [range(l // c, (h - 1) // c + 1) if h > l else range(0) for l, h, c in zip(lo, hi, self.chunks)]
         for idx in np.ndindex(*[len(r) for r in ranges]):
             cid = tuple(r[i] for r, i in zip(ranges, idx))
+            if self._read_into(cid, lo, hi, out):
+                continue
             ch = self._chunk(cid)
             src, dst = [], []
             for k, (c, l, h) in enumerate(zip(self.chunks, lo, hi)):
