@@ -314,7 +314,7 @@ inline int64_t env_i64(const char* name, int64_t dflt, int64_t lo, int64_t hi) {
 // Tunables of the host-pointer path (columns per staged block, streams in the ring).  Blocks
 // grow geometrically from XCAPE_B200_FIRST_CHUNK_COLS to XCAPE_B200_CHUNK_COLS: a small first block
 // gets the GPU busy after ~0.3 ms of H2D, large later blocks keep per-kernel tails rare.
-inline int64_t chunk_cols() { return env_i64("XCAPE_B200_CHUNK_COLS", 1 << 18, 1024, 1 << 26); }
+inline int64_t chunk_cols() { return env_i64("XCAPE_B200_CHUNK_COLS", 1 << 17, 1024, 1 << 26); }   // r2 sweep (profiles/r2_probe_e2e_plans2.txt): 131072 -> 10.0 ms per ERA5 field, 262144 -> 10.7, 524288 -> 11.0
 inline int64_t first_chunk_cols() { return env_i64("XCAPE_B200_FIRST_CHUNK_COLS", 1 << 16, 1024, 1 << 26); }
 inline int ring_streams() { return (int)env_i64("XCAPE_B200_STREAMS", 4, 1, kMaxStreams); }
 
