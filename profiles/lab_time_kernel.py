@@ -18,7 +18,7 @@ source = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 prec = sys.argv[4] if len(sys.argv) > 4 else 'faithful'
 kw = {'grid': (721, 1440)} if cfg == 'C5' else {}
-d = make_soundings(cfg, winds=False, **kw)
+d = make_soundings(cfg, winds=False, shuffle=bool(int(os.environ.get('LAB_SHUFFLE', '0'))), active=bool(int(os.environ.get('LAB_ACTIVE', '1'))), **kw)
 dev = torch.device('cuda', 0)
 p1d = d['p'].ndim == 1
 t = torch.from_numpy(d['t']).to(dev).t().contiguous()
@@ -44,5 +44,5 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
 out = run(return_counters=True)
 h = hashlib.sha1(b''.join(o.cpu().numpy().tobytes() for o in out)).hexdigest()[:16]
-print(f'{os.path.basename(_lib.LIB_PATH)} {cfg} source={source} {prec}: {ms:.3f} ms/launch, {t.shape[1] / ms * 1e-3:.3e} col/s, '
+print(f'{os.path.basename(_lib.LIB_PATH)} {cfg} source={source} {prec} sort={os.environ.get("XCAPE_B200_SORT", "-")} shuffle={os.environ.get("LAB_SHUFFLE", "0")} active={os.environ.get("LAB_ACTIVE", "1")}: {ms:.3f} ms/launch, {t.shape[1] / ms * 1e-3:.3e} col/s, '
       f'iters/col {float(out[5].double().mean()):.1f}, cape mean {float(out[0].double().mean()):.4f}, sha1 {h}', flush=True)

@@ -174,6 +174,32 @@ def test_two_column_kernel_matches_one_column_kernel(core, cfg, vertical_lev, nc
             assert np.array_equal(a, b), f'{cfg} {source} adiabat {adiabat}: {name} differs in {(a != b).sum()} columns'
 
 
+@pytest.mark.parametrize('cfg,vertical_lev,ncol', [('C1', 'sigma', 1000), ('C2', 'pressure', 8191), ('C2', 'pressure', 20001), ('C5', 'sigma', 1537)])
+@pytest.mark.parametrize('source', SOURCES)
+def test_sorted_execution_matches_storage_order(core, cfg, vertical_lev, ncol, source, monkeypatch):
+    """Sorted execution of the faithful kernel (cape_sort.cuh: source parcels + keys, counting sort by (start level,
+    theta-e), ascent in key order) only decides which columns share a warp: every output, status and iteration
+    counter included, equals the storage-order run bit for bit — gated columns, odd column counts and the
+    level-window status (more levels than shipped) included."""
+    from xcape_b200.cape_cuda import cape as cape_cuda
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings(cfg, cols=(0, ncol), active=False, **({'grid': (721, 1440)} if cfg == 'C5' else {}))
+    p1d = d['p'].ndim == 1
+    src = {'surface': 1, 'most-unstable': 2, 'mixed-layer': 3}[source]
+
+    def run(adiabat):
+        p = d['p'] if p1d else d['p'].T
+        return cape_cuda(p, d['t'].T, d['td'].T, d['ps'], d['ts'], d['tds'], 1 if p1d else 0, None, src, 500., adiabat, 500.,
+                         2 if p1d else 1, return_counters=True)
+    for adiabat in (1, 2, 3, 4):
+        monkeypatch.setenv('XCAPE_B200_SORT', '1')
+        srt = run(adiabat)
+        monkeypatch.setenv('XCAPE_B200_SORT', '0')
+        sto = run(adiabat)
+        for a, b, name in zip(srt, sto, ('cape', 'cin', 'mulev', 'zmulev', 'status', 'n_iter')):
+            assert np.array_equal(a, b, equal_nan=True), f'{cfg} {source} adiabat {adiabat}: {name} differs in {(a != b).sum()} columns'
+
+
 @pytest.mark.parametrize('cfg,source,ml_depth,vertical_lev', [
     ('C2', 'most-unstable', 500., 'pressure'),      # BASELINE configs[1]: 1 038 240 columns x 37 levels
     ('C3', 'mixed-layer', 500., 'sigma'),           # configs[2]: 1 905 141 columns x 50 levels
@@ -471,6 +497,30 @@ def test_srh_two_call_form_matches_fused_and_oracle(core, oracle_mod, cfg, type_
         assert np.abs(np.asarray(g) - r).max() <= 2e-5
 
 
+@pytest.mark.parametrize('cfg,vertical_lev', [('C3', 'sigma'), ('C2', 'pressure'), ('C5', 'sigma')])
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+@pytest.mark.parametrize('precision', ['faithful', 'fast'])
+def test_srh_tile_kernel_matches_relayout_path(core, cfg, vertical_lev, dtype, precision, monkeypatch):
+    """Reference-layout (level-last) input is read in place by the tile kernel (srh_tile.cuh); XCAPE_B200_SRH_TILE=0
+    re-lays the fields out and runs the level-major kernel.  Same per-column arithmetic, so every output is the
+    same bit for bit — odd column counts (a partial tile), odd and even level counts, start levels above the
+    surface (pressure grids), non-monotone columns (EXACT work list) and float64 inputs included."""
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings(cfg, cols=(0, 12345), **({'grid': (721, 1440)} if cfg == 'C5' else {}))
+    p = d['p'].copy()
+    if vertical_lev == 'sigma':
+        p[::5, 7] = p[::5, 6]                         # duplicate level
+        p[1::11, 12] = p[1::11, 10] + 1.0             # out of order
+    args = tuple(a.astype(dtype) for a in (p, d['t'], d['td'], d['u'], d['v'], d['ps'], d['ts'], d['tds'], d['us'], d['vs']))
+    out = {}
+    for tile in ('1', '0'):
+        monkeypatch.setenv('XCAPE_B200_SRH_TILE', tile)
+        out[tile] = core.calc_srh(*args, depth=3000, vertical_lev=vertical_lev, output_var='all', method='cuda', precision=precision)
+    assert len(out['1']) == len(out['0']) == 8
+    for i, (a, b) in enumerate(zip(out['1'], out['0'])):
+        assert np.array_equal(a, b, equal_nan=True), f'output {i}: {(a != b).sum()} elements differ, max {np.nanmax(np.abs(a - b))}'
+
+
 def test_srh_nonmonotone_pressure_takes_exact_path(core, oracle_mod):
     """Duplicate / out-of-order pressure levels: the kernel's EXACT path must reproduce
     DINTERP2DZ's top-down 'highest bracket wins' search literally."""
@@ -713,12 +763,14 @@ def test_srh_fast_precision(core, oracle_mod, cfg, vertical_lev):
 # ------------------------------------------------------------------ garbage in: never hang, never crash
 @pytest.mark.timeout(180)
 @pytest.mark.parametrize('vertical_lev', ['sigma', 'pressure'])
-def test_garbage_inputs_terminate_and_match_oracle(core, oracle_mod, vertical_lev):
-    """Fill values, NaN, inf, zero / negative / unordered pressures: every call returns promptly
+@pytest.mark.parametrize('sort', ['0', '1'])
+def test_garbage_inputs_terminate_and_match_oracle(core, oracle_mod, vertical_lev, sort, monkeypatch):
+    """(In storage order and through the sorted execution of the faithful kernel.)  Fill values, NaN, inf, zero / negative / unordered pressures: every call returns promptly
     (no thread may spin: status 3 guards), never raises, and — because oracle and kernel share the
     arithmetic contract down to NaN propagation — still agrees with the oracle bit for bit."""
     from xcape_b200.cape_cuda import cape as cape_cuda
     from xcape_b200.synthetic import make_soundings
+    monkeypatch.setenv('XCAPE_B200_SORT', sort)
     cfg = 'C3' if vertical_lev == 'sigma' else 'C2'
     d = make_soundings(cfg, cols=(0, 4096))
     rng = np.random.default_rng(5)

@@ -184,7 +184,14 @@ int cape_device(const void* p, const void* t, const void* td, const void* ps, co
   }
   a.ncol = ncol; a.ld = ld; a.nlev = nlev; a.pinc = pinc; a.ml_depth = ml_depth;
   a.cape = cape; a.cin = cin; a.zout = zmulev; a.mulvl = mulev; a.status = status; a.n_iter = n_iter;
-  if (precision == XCAPE_FAITHFUL) return launch_cape_faithful(a, source, adiabat, p_is_1d != 0, s);
+  if (precision == XCAPE_FAITHFUL) {
+    if (const size_t nb = cape_sort_scratch_bytes(ncol, nlev)) {    // sorted execution (cape_sort.cuh)
+      char* blob;
+      XC_CUDA(sc.alloc(&blob, nb));
+      a.sort_scratch = blob;
+    }
+    return launch_cape_faithful(a, source, adiabat, p_is_1d != 0, s);
+  }
   if (precision == XCAPE_FAST || precision == XCAPE_FAST_OPTIMISTIC) {
     a.keep_secant = (precision == XCAPE_FAST_OPTIMISTIC) ? 1 : 0;
     return launch_cape_fast(a, source, adiabat, p_is_1d != 0, s);
@@ -224,7 +231,14 @@ int srh_device_t(const void* p, const void* t, const void* td, const void* u, co
   int rc;
   const void* q;
   int64_t ld = ncol, l2 = ncol;
-  {
+  // reference layout (level-last), surface first: read in place by the tile kernel (srh_tile.cuh) — no relayout.
+  // XCAPE_B200_SRH_TILE=0 selects relayout + level-major kernel (A/B, tests).
+  const char* tile_env = getenv("XCAPE_B200_SRH_TILE");
+  const bool tile = base_layout(layout) == XCAPE_LEVEL_LAST && !top_first(layout) && !(tile_env && tile_env[0] == '0');
+  if (tile) {
+    a.t = (const T*)t; a.td = (const T*)td; a.u = (const T*)u; a.v = (const T*)v; a.p = (const T*)p;
+    a.lev_stride = 1; a.col_stride = nlev;
+  } else {
     if ((rc = canon3d_same(t, dtype, layout, ncol, nlev, ld_in, sc, &q, &ld, s))) return rc; a.t = (const T*)q;
     if ((rc = canon3d_same(td, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.td = (const T*)q;
     if ((rc = canon3d_same(u, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.u = (const T*)q;
@@ -244,7 +258,7 @@ int srh_device_t(const void* p, const void* t, const void* td, const void* u, co
   a.ncol = ncol; a.ld = ld; a.nlev = nlev; a.depth = depth; a.aglh0 = aglh0;
   a.srh_rm = srh_rm; a.srh_lm = srh_lm; a.rm = rm; a.lm = lm; a.mean6 = mean6;
   { int32_t* wl; int* wc; XC_CUDA(sc.alloc(&wl, (size_t)ncol)); XC_CUDA(sc.alloc(&wc, (size_t)1)); a.work_list = wl; a.work_count = wc; }
-  return launch_srh(a, p_is_1d != 0, s);
+  return tile ? launch_srh_tile(a, p_is_1d != 0, s) : launch_srh(a, p_is_1d != 0, s);
 }
 
 // srh.srh signature: heights are given (float64 from stdheight in the reference)

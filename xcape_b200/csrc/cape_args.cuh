@@ -1,8 +1,20 @@
 // cape_args.cuh — argument block of the CAPE kernels (shared by the launchers in api.cu and the kernel TUs).
 #pragma once
+#include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace xc {
+
+// Sorted execution of the faithful kernel (cape_sort.cuh): source parcels found in storage order and written to
+// per-column records; the ascent kernel then takes its columns in the order `perm`, which groups columns whose parcels
+// start on the same level with (almost) the same theta-e — lanes of a warp then need the same pass counts.
+struct CapeSorted {
+  const int32_t* __restrict__ perm;   // [ncol] column handled at position i; nullptr = storage order, no records
+  const int4* __restrict__ rec_i;     // {ks, k, mulvl, st | active << 4 | zout_is_sentinel << 5}
+  const float4* __restrict__ rec_a;   // {th2, pi2, p2, t2}
+  const float4* __restrict__ rec_b;   // {qv2, b2, z, prev_p}
+  const float2* __restrict__ rec_c;   // {prev_pi, prev_thv}
+};
 
 struct CapeArgs {
   const float* __restrict__ p;     // P1D: [nlev] hPa; else level-major [nlev][ld]
@@ -28,6 +40,8 @@ struct CapeArgs {
                                    // a column still ascending after the last one gets status 4 (internal) and is redone
   const float* __restrict__ pl_pi; // P1D only, nullable: Exner function of the nlev pressure levels, precomputed once per
                                    // call by exner_table_kernel with the same SPEC pow (bit-identical, saves a pow per level)
+  void* sort_scratch;              // faithful kernel only, nullable: cape_sort_scratch_bytes() bytes -> sorted execution
+  CapeSorted sorted;               // filled by the launcher from sort_scratch
 };
 
 }  // namespace xc

@@ -8,7 +8,9 @@
 #include "cape_kernel.cuh"
 #if !defined(XC_FAST_TU) && !defined(XC_FAST_RELAXED_TU)
 #include "cape_kernel2.cuh"
+#include "cape_sort.cuh"
 #include <cstdlib>
+#include <mutex>
 #endif
 
 namespace xc {
@@ -61,7 +63,31 @@ static int launch(const CapeArgs& a, cudaStream_t s) {
     const int64_t pairs = (a.ncol + 1) / 2;
     const int64_t blocks2 = (pairs + threads2 - 1) / threads2;
     if (blocks2 <= 0) return XCAPE_OK;
-    cape_kernel2<MathPolicy, SOURCE, ADIABAT, P1D><<<(unsigned)blocks2, threads2, 0, s>>>(a);
+    if (a.sort_scratch) {
+      // sorted execution (cape_sort.cuh): source parcels + keys, per-window sort, then the ascent in key order
+      SortBufs b = sort_carve(a.sort_scratch, a.ncol, a.nlev);
+      const char* tb = getenv("XCAPE_B200_SORT_TBIN");               // lab knob: theta-e bin width of the sort key, K
+      const float tbin = tb ? (float)atof(tb) : 4.0f;
+      b.inv_tbin = 1.0f / (tbin > 0.01f ? tbin : 4.0f);
+      cape_source_kernel<MathPolicy, SOURCE, P1D><<<(unsigned)((a.ncol + 127) / 128), 128, 0, s>>>(a, b);
+      XC_LAUNCH_CHECK();
+      static std::once_flag smem_once[64];
+      int dev = 0;
+      XC_CUDA(cudaGetDevice(&dev));
+      cudaError_t attr_err = cudaSuccess;
+      std::call_once(smem_once[dev & 63], [&] {
+        attr_err = cudaFuncSetAttribute(cape_window_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortWindow * 8);
+      });
+      XC_CUDA(attr_err);
+      cape_window_sort_kernel<<<(unsigned)((a.ncol + kSortWindow - 1) / kSortWindow), kSortThreads, kSortWindow * 8, s>>>(b.key, b.perm, a.ncol);
+      XC_LAUNCH_CHECK();
+      CapeArgs as = a;
+      as.sorted.perm = b.perm; as.sorted.rec_i = b.rec_i; as.sorted.rec_a = b.rec_a; as.sorted.rec_b = b.rec_b; as.sorted.rec_c = b.rec_c;
+      cape_kernel2<MathPolicy, 1, ADIABAT, P1D, true><<<(unsigned)blocks2, threads2, 0, s>>>(as);
+      XC_LAUNCH_CHECK();
+      return XCAPE_OK;
+    }
+    cape_kernel2<MathPolicy, SOURCE, ADIABAT, P1D, false><<<(unsigned)blocks2, threads2, 0, s>>>(a);
     XC_LAUNCH_CHECK();
     return XCAPE_OK;
   }
@@ -86,6 +112,16 @@ static int launch_adiabat(const CapeArgs& a, int adiabat, cudaStream_t s) {
 }
 
 #if !defined(XC_FAST_TU) && !defined(XC_FAST_RELAXED_TU)
+// bytes of scratch the sorted execution of the faithful kernel wants for this call; 0 = run in storage order.
+// XCAPE_B200_SORT=0 disables it, =1 forces it for any size (tests); by default calls of >= 8192 columns are sorted.
+size_t cape_sort_scratch_bytes(int64_t ncol, int nlev) {
+  const char* e = getenv("XCAPE_B200_SORT");
+  const char* which = getenv("XCAPE_B200_CAPE_KERNEL");
+  if ((which && which[0] == '1') || (e && e[0] == '0')) return 0;
+  if (ncol >= (int64_t)1 << 31 || ncol < 2) return 0;
+  if (!(e && e[0] == '1') && ncol < 8192) return 0;
+  return sort_scratch_bytes(ncol, nlev);
+}
 int launch_exner_table(const float* p_hpa, float* pi, int nlev, cudaStream_t s) {
   exner_table_kernel<MathSpec><<<(nlev + 127) / 128, 128, 0, s>>>(p_hpa, pi, nlev);
   XC_LAUNCH_CHECK();

@@ -115,23 +115,28 @@ __device__ __forceinline__ f2 vmoist_arg(f2 t2, f2 p2, f2 qt, f2 t1, f2 qv1, f2 
     const f2 w = vsub(qt, qv2);
     ql2 = make_float2(fmaxf(w.x, 0.0f), fmaxf(w.y, 0.0f));
   }
-  const f2 tbar = vmul(vadd(t1, t2), 0.5f);
-  const f2 qvbar = vmul(vadd(qv1, qv2), 0.5f);
-  const f2 qlbar = PSEUDO ? vmul(ql2, 0.5f) : vmul(vadd(ql1, ql2), 0.5f);       // ql1 = 0: 0 + x = x
-  const f2 lhv = sadd(vmul(tbar, -cc::lv2), cc::lv1);                          // lv1 - lv2*tbar
-  const f2 rm = sadd(vmul(qvbar, cc::rv), cc::rd);
-  f2 cpm = sadd(sadd(vmul(qvbar, cc::cpv), cc::cp), vmul(qlbar, cc::cpl));
+  // The reference's layer means tbar = 0.5 (t1 + t2), qvbar, qlbar, qibar are not formed: a multiplication by 0.5 is
+  // exact, so it commutes with every rounding that follows — rv * (0.5 s) and (0.5 rv) * s are the same real number, hence
+  // the same binary32; lv1 - lv2 * tbar is half of 2 lv1 - lv2 * s; and in lhv * dql / (cpm * tbar) numerator and
+  // denominator are both doubled, which leaves the correctly rounded quotient unchanged.  (The window admits the
+  // sub-step only when no product here can be subnormal: 180 <= s_t <= 800, qt = 0 or qt >= 1e-18.)
+  const f2 st = vadd(t1, t2);
+  const f2 sq = vadd(qv1, qv2);
+  const f2 sl = PSEUDO ? ql2 : vadd(ql1, ql2);                                 // ql1 = 0: 0 + x = x
+  const f2 lhv2 = sadd(vmul(st, -cc::lv2), 2.0f * cc::lv1);                    // 2 (lv1 - lv2*tbar)
+  const f2 rm = sadd(vmul(sq, 0.5f * cc::rv), cc::rd);
+  f2 cpm = sadd(sadd(vmul(sq, 0.5f * cc::cpv), cc::cp), vmul(sl, 0.5f * cc::cpl));
   const f2 dql = PSEUDO ? ql2 : vsub(ql2, ql1);
   f2 arg;
   if (ICE) {
-    const f2 qibar = PSEUDO ? vmul(qi2, 0.5f) : vmul(vadd(qi1, qi2), 0.5f);
-    const f2 lhs = sadd(vmul(tbar, -cc::ls2), cc::ls1);
-    cpm = sadd(cpm, vmul(qibar, cc::cpi));
-    const f2 den = vmul(cpm, tbar);
+    const f2 si = PSEUDO ? qi2 : vadd(qi1, qi2);
+    const f2 lhs2 = sadd(vmul(st, -cc::ls2), 2.0f * cc::ls1);
+    cpm = sadd(cpm, vmul(si, 0.5f * cc::cpi));
+    const f2 den2 = vmul(cpm, st);                                             // 2 cpm tbar
     const f2 dqi = PSEUDO ? qi2 : vsub(qi2, qi1);
-    arg = vadd(vdiv_fast(vmul(lhv, dql), den), vdiv_fast(vmul(lhs, dqi), den));
+    arg = vadd(vdiv_fast(vmul(lhv2, dql), den2), vdiv_fast(vmul(lhs2, dqi), den2));
   } else {
-    arg = vdiv_fast(vmul(lhv, dql), vmul(cpm, tbar));
+    arg = vdiv_fast(vmul(lhv2, dql), vmul(cpm, st));
   }
   return sadd(arg, vmul(vadd(vdiv_fast(rm, cpm), -cc::rddcp), logp));
 }
@@ -184,6 +189,25 @@ __device__ __forceinline__ void col2_init(const CapeArgs& a, int64_t c, Col2& C)
   if (!C.active && a.more_levels) C.st = 4;         // the parcel starts on the last level shipped: the column is taller
 }
 
+// sorted execution (cape_sort.cuh): the state col2_init left in the column's record
+__device__ __forceinline__ void col2_load(const CapeArgs& a, int64_t c, Col2& C) {
+  C.c = c; C.live = (c >= 0 && c < a.ncol); C.active = false;
+  C.st = 0; C.iters = 0; C.mulvl = 0; C.zout = 0.0f; C.cape = 0.0f; C.cin = 0.0f; C.narea = 0.0f; C.z = 0.0f; C.b2 = 0.0f;
+  C.th2 = C.pi2 = C.p2 = C.t2 = C.qv2 = C.ql2 = C.qi2 = C.qt = 0.0f;
+  C.prev_p = C.prev_pi = C.prev_thv = 0.0f; C.ks = 1; C.nk = 1; C.k = 1; C.lev_next = 0;
+  if (!C.live) return;
+  const int4 ri = a.sorted.rec_i[c];
+  const float4 ra = a.sorted.rec_a[c];
+  const float4 rb = a.sorted.rec_b[c];
+  const float2 rc = a.sorted.rec_c[c];
+  C.ks = ri.x; C.nk = a.nlev - ri.x + 2; C.k = ri.y; C.mulvl = ri.z;
+  C.st = ri.w & 15; C.active = (ri.w & 16) != 0; C.zout = (ri.w & 32) ? -999999.0f : 0.0f;
+  C.th2 = ra.x; C.pi2 = ra.y; C.p2 = ra.z; C.t2 = ra.w;
+  C.qv2 = rb.x; C.qt = rb.x; C.b2 = rb.y; C.z = rb.z; C.prev_p = rb.w;
+  C.prev_pi = rc.x; C.prev_thv = rc.y;
+  C.lev_next = C.ks + C.k - 2;
+}
+
 // f90:403-415 — the layer's environment, sub-step count, and the per-layer windows
 template <class M, bool P1D, bool ICE>
 __device__ __forceinline__ void col2_layer_begin(const CapeArgs& a, Col2& C, Layer2& Y) {
@@ -223,7 +247,7 @@ __device__ __forceinline__ void col2_sub_begin(Col2& C, const Layer2& Y, Sub2& S
     // all operands normal and far from the range ends: the unguarded cores give what M::pow / M::log / `/` give
     C.pi2 = __double2float_rn(spec_exp_core(__dmul_rn((double)cc::rddcp, spec_log_core((double)(C.p2 * cc::rp00)))));
     S.logp = __double2float_rn(spec_log_core((double)fdiv_fast(C.p2, S.p1)));
-    S.window = (Y.tmax >= 100.0f) && (S.t1 >= 90.0f) && (S.t1 <= 400.0f) && (C.qt >= 0.0f) && (C.qt <= 1.0f) &&
+    S.window = (Y.tmax >= 100.0f) && (S.t1 >= 90.0f) && (S.t1 <= 400.0f) && (C.qt == 0.0f || C.qt >= 1e-18f) && (C.qt <= 1.0f) &&
                (S.ql1 <= 1.0f) && (S.qi1 <= 1.0f) && (fabsf(S.th1) < CUDART_INF_F);
   } else {
     C.pi2 = M::pow(C.p2 * cc::rp00, cc::rddcp);
@@ -313,7 +337,9 @@ __device__ __forceinline__ void col2_store(const CapeArgs& a, const Col2& C) {
 #ifndef XC_CAPE2_MIN_BLOCKS
 #define XC_CAPE2_MIN_BLOCKS 5    // <= 102 registers.  Measured per ERA5 field (ms): 4 CTAs 8.88, 5 CTAs 8.66, 6 CTAs 8.71, 3 x 256 threads 8.63:
 #endif                           // the kernel is bound by FMA-pipe / register-file bandwidth, not by occupancy
-template <class M, int SOURCE, int ADIABAT, bool P1D>
+// SORTED: the columns come in the order a.sorted.perm with their source parcels in records (cape_sort.cuh); SOURCE is
+// then irrelevant (instantiated with 1 only)
+template <class M, int SOURCE, int ADIABAT, bool P1D, bool SORTED>
 __global__ void __launch_bounds__(XC_CAPE2_THREADS, XC_CAPE2_MIN_BLOCKS) cape_kernel2(const CapeArgs a) {
   exp32_smem_fill();
   constexpr bool ICE = (ADIABAT == 3 || ADIABAT == 4);
@@ -322,8 +348,13 @@ __global__ void __launch_bounds__(XC_CAPE2_THREADS, XC_CAPE2_MIN_BLOCKS) cape_ke
   if (c0 >= a.ncol) return;
 
   Col2 A, B;
-  col2_init<M, SOURCE, P1D>(a, c0, A);
-  col2_init<M, SOURCE, P1D>(a, c0 + 1, B);
+  if (SORTED) {                                     // positions 2t, 2t+1 of the order, state from the records
+    col2_load(a, a.sorted.perm[c0], A);
+    col2_load(a, (c0 + 1 < a.ncol) ? a.sorted.perm[c0 + 1] : -1, B);
+  } else {
+    col2_init<M, SOURCE, P1D>(a, c0, A);
+    col2_init<M, SOURCE, P1D>(a, c0 + 1, B);
+  }
 
   for (int L = 0; L < a.nlev; ++L) {
     if (!(A.active || B.active)) break;
@@ -360,21 +391,20 @@ __global__ void __launch_bounds__(XC_CAPE2_THREADS, XC_CAPE2_MIN_BLOCKS) cape_ke
         const f2 ql1 = make_float2(wa ? SA.ql1 : SB.ql1, wb ? SB.ql1 : SA.ql1);
         const f2 qi1 = make_float2(wa ? SA.qi1 : SB.qi1, wb ? SB.qi1 : SA.qi1);
         const f2 logp = make_float2(wa ? SA.logp : SB.logp, wb ? SB.logp : SA.logp);
-        const f2 tmx = make_float2(wa ? YA.tmax : YB.tmax, wb ? YB.tmax : YA.tmax);
-        const f2 tc = vmul(vadd(tmx, 90.0f), 0.5f);
-        const f2 hw = vmul(vmul(vadd(tmx, -90.0f), 0.5f), 0.999f);   // shrunk: tc +- hw lies inside [90, tmax] for any rounding
+        // the window's accumulators are shared by the two halves (leaving it is rare, and the general loop is always right):
+        // 90 <= every t2 <= the smaller tmax, every |arg| <= 2^-6
+        const float tmx = fminf(wa ? YA.tmax : YB.tmax, wb ? YB.tmax : YA.tmax);
         f2 thlast = th1;
-        f2 dev_t = splat(0.0f), dev_a = splat(0.0f);
+        float t_hi = 90.0f, t_lo = 400.0f, a_hi = 0.0f;
         f2 t2, th2, qv2, ql2, qi2;
         int lx = 101, ly = 101;                     // `left` at the last pass that ended with the half still moving
         int left = 100;
         bool mx, my;
         do {
           t2 = vmul(thlast, pi2);
-          const f2 dt = ssub(t2, tc);
-          dev_t.x = fmaxf(dev_t.x, fabsf(dt.x)); dev_t.y = fmaxf(dev_t.y, fabsf(dt.y));
+          t_hi = fmaxf(t_hi, fmaxf(t2.x, t2.y)); t_lo = fminf(t_lo, fminf(t2.x, t2.y));      // FMNMX3
           const f2 arg = vmoist_arg<ICE, PSEUDO>(t2, p2, qt, t1, qv1, ql1, qi1, logp, qv2, ql2, qi2);
-          dev_a.x = fmaxf(dev_a.x, fabsf(arg.x)); dev_a.y = fmaxf(dev_a.y, fabsf(arg.y));
+          a_hi = fmaxf(a_hi, fmaxf(fabsf(arg.x), fabsf(arg.y)));
           th2 = vmul(th1, vexp32_tiny(arg));
           const f2 d = ssub(th2, thlast);
           const f2 step = vmul(d, 0.3f);
@@ -385,8 +415,9 @@ __global__ void __launch_bounds__(XC_CAPE2_THREADS, XC_CAPE2_MIN_BLOCKS) cape_ke
           left = left - 1;
         } while ((mx || my) && left != 0);
         // pass k runs with left = 101 - k: the half took (101 - l) + 1 passes, or was still moving at pass 100 (l == 1)
+        const bool left_window = !(t_lo >= 90.0f) || !(t_hi <= tmx) || !(a_hi <= 0.015625f);
         if (wa) {
-          genA = !(dev_t.x <= hw.x) || !(dev_a.x <= 0.015625f);
+          genA = left_window;
           if (!genA) {
             A.t2 = t2.x; A.th2 = th2.x; A.qv2 = qv2.x; A.ql2 = ql2.x; A.qi2 = qi2.x;
             iA = 102 - lx;
@@ -394,7 +425,7 @@ __global__ void __launch_bounds__(XC_CAPE2_THREADS, XC_CAPE2_MIN_BLOCKS) cape_ke
           }
         }
         if (wb) {
-          genB = !(dev_t.y <= hw.y) || !(dev_a.y <= 0.015625f);
+          genB = left_window;
           if (!genB) {
             B.t2 = t2.y; B.th2 = th2.y; B.qv2 = qv2.y; B.ql2 = ql2.y; B.qi2 = qi2.y;
             iB = 102 - ly;

@@ -1,0 +1,117 @@
+// cape_sort.cuh — sorted execution of the faithful CAPE kernel.
+//
+// Why (profiles/divergence_sorted_model.py): the moist iteration of a sub-step runs until the slowest
+// of a warp's 64 columns has converged, and a layer takes as many sub-steps as its thickest column needs.  On an
+// ERA5-shape field in storage order a warp executes 1.17 x the mean passes of its columns (1.30 x when neighbouring
+// columns are unrelated).  The pass counts of a column are a function of the parcel it lifts — the level it starts
+// from, its theta-e (which names the moist adiabat it follows above the LCL) — and of the surface pressure (which sets
+// the sub-step count of every layer on sigma grids, of the first layer on pressure grids).  Columns grouped by
+// (start level, theta-e in 4 K bins, surface pressure) converge together: 1.06-1.07 x the mean, whatever the storage
+// order was.  Columns that do not ascend at all (ts <= 0 degC gate, parcel on the top level) go to the end of their
+// window, so whole warps of them leave at once instead of idling beside working lanes.
+//
+// The order is established inside WINDOWS of 16384 consecutive columns, not globally: the ascent kernel's per-level
+// loads become gathers (a 32-byte sector for 4 bytes), and the other seven columns of a sector are then lifted by
+// CTAs of the same window at about the same time, so the sector is served by L2 instead of crossing HBM eight times
+// (a global order was measured: ERA5 pressure levels fine, HRRR 50 sigma levels 15.8 -> 17.4 ms).  A window is also
+// what one CTA can sort in shared memory.
+//
+// Pipeline (all on the caller's stream, scratch from the caller):
+//   1. cape_source_kernel   storage order, coalesced: gate, start level, source parcel (the scalar code of
+//                           cape_kernel.cuh, run once per column) -> parcel record + 32-bit key
+//   2. cape_window_sort_kernel  one CTA per window: bitonic sort of (key << 32 | column) in shared memory -> perm[]
+//   3. cape_kernel2<SORTED> thread t lifts columns perm[2t], perm[2t+1] from their records
+// The key only decides which columns share a warp; results are per-column and bit-identical to the unsorted run
+// (tests/test_gpu_parity.py::test_sorted_execution_matches_storage_order).  The sort is deterministic.
+#pragma once
+#include "cape_kernel2.cuh"
+
+namespace xc {
+
+constexpr int kSortWindow = 16384;             // columns per window: 128 KB of shared memory for the 64-bit sort elements
+constexpr int kSortThreads = 1024;
+
+struct SortBufs {
+  int4* rec_i; float4* rec_a; float4* rec_b; float2* rec_c;
+  uint32_t* key; int32_t* perm;
+  float inv_tbin;                               // 1 / (theta-e bin width, K)
+};
+
+inline size_t sort_align(size_t x) { return (x + 255) & ~(size_t)255; }
+inline size_t sort_scratch_bytes(int64_t ncol, int /*nlev*/) {
+  const size_t n = (size_t)ncol;
+  return sort_align(16 * n) * 3 + sort_align(8 * n) + sort_align(4 * n) * 2;
+}
+inline SortBufs sort_carve(void* blob, int64_t ncol, int /*nlev*/) {
+  char* q = (char*)blob;
+  const size_t n = (size_t)ncol;
+  SortBufs b;
+  b.rec_i = (int4*)q; q += sort_align(16 * n);
+  b.rec_a = (float4*)q; q += sort_align(16 * n);
+  b.rec_b = (float4*)q; q += sort_align(16 * n);
+  b.rec_c = (float2*)q; q += sort_align(8 * n);
+  b.key = (uint32_t*)q; q += sort_align(4 * n);
+  b.perm = (int32_t*)q;
+  return b;
+}
+
+// Bolton's theta-e of the parcel (p Pa, t K, q kg/kg) with approximate intrinsics: a grouping key, not a result
+__device__ __forceinline__ float thetae_key(float p, float t, float q) {
+  q = fminf(fmaxf(q, 1e-9f), 0.2f);
+  const float e = __fdividef(q * p, 0.622f + q) * 0.01f;                       // vapour pressure, hPa
+  const float tl = __fdividef(2840.0f, 3.5f * __logf(t) - __logf(e) - 4.805f) + 55.0f;
+  return t * __powf(__fdividef(100000.0f, p), 0.2854f * (1.0f - 0.28f * q)) *
+         __expf((__fdividef(3376.0f, tl) - 2.54f) * q * (1.0f + 0.81f * q));
+}
+
+// key: start level (8 bits) | theta-e bin from 200 K (10 bits; bin width 1 / inv_tbin K) | surface pressure in Pa / 8 (14 bits);
+// 0xFFFFFFFF = no ascent.  NaN / out-of-range inputs clamp into some bin — any grouping is a valid grouping.
+template <class M, int SOURCE, bool P1D>
+__global__ void __launch_bounds__(128) cape_source_kernel(const CapeArgs a, const SortBufs b) {
+  exp32_smem_fill();
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.ncol) return;
+  Col2 C;
+  col2_init<M, SOURCE, P1D>(a, c, C);
+  const int flags = C.st | (C.active ? 16 : 0) | (C.zout != 0.0f ? 32 : 0);
+  b.rec_i[c] = make_int4(C.ks, C.k, C.mulvl, flags);
+  b.rec_a[c] = make_float4(C.th2, C.pi2, C.p2, C.t2);
+  b.rec_b[c] = make_float4(C.qv2, C.b2, C.z, C.prev_p);
+  b.rec_c[c] = make_float2(C.prev_pi, C.prev_thv);
+  uint32_t key = 0xFFFFFFFFu;
+  if (C.active) {
+    const float x = (thetae_key(C.p2, C.t2, C.qv2) - 200.0f) * b.inv_tbin;
+    const uint32_t bin = (uint32_t)fminf(fmaxf(x, 0.0f), 1023.0f);             // NaN -> 0
+    const uint32_t lev = (uint32_t)min(max(C.lev_next, 0), 255);
+    const uint32_t psq = (uint32_t)fminf(fmaxf(a.ps[c] * 12.5f, 0.0f), 16383.0f);
+    key = (lev << 24) | (bin << 14) | psq;
+    if (key == 0xFFFFFFFFu) key = 0xFFFFFFFEu;
+  }
+  b.key[c] = key;
+}
+
+// one CTA sorts one window: elements (key << 32 | index in window), bitonic network in shared memory
+__global__ void __launch_bounds__(kSortThreads) cape_window_sort_kernel(const uint32_t* __restrict__ key, int32_t* __restrict__ perm,
+                                                                       int64_t ncol) {
+  extern __shared__ unsigned long long sk[];
+  const int64_t w0 = (int64_t)blockIdx.x * kSortWindow;
+  const int count = (int)min((int64_t)kSortWindow, ncol - w0);
+  for (int i = threadIdx.x; i < kSortWindow; i += kSortThreads)
+    sk[i] = (i < count) ? (((unsigned long long)key[w0 + i] << 32) | (unsigned)i) : ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= kSortWindow; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < kSortWindow / 2; t += kSortThreads) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i + j;
+        const unsigned long long x = sk[i], y = sk[l];
+        const bool asc = (i & k) == 0;
+        if ((x > y) == asc) { sk[i] = y; sk[l] = x; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < count; i += kSortThreads) perm[w0 + i] = (int32_t)(w0 + (int64_t)(sk[i] & 0xFFFFFFFFull));
+}
+
+}  // namespace xc

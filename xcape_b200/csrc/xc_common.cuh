@@ -39,6 +39,7 @@ inline size_t esize(int dtype) { return dtype == XCAPE_F64 ? 8 : 4; }
 
 // entry points of the per-TU kernel launchers
 int launch_cape_faithful(const struct CapeArgs& a, int source, int adiabat, bool p1d, cudaStream_t s);
+size_t cape_sort_scratch_bytes(int64_t ncol, int nlev);
 int launch_cape_fast(const struct CapeArgs& a, int source, int adiabat, bool p1d, cudaStream_t s);
 int launch_exner_table(const float* p_hpa, float* pi, int nlev, cudaStream_t s);
 int launch_cape_fast_relaxed(const struct CapeArgs& a, int source, int adiabat, bool p1d, cudaStream_t s);
