@@ -4,7 +4,7 @@ set -x
 cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 {
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "sorted_execution or garbage or full_field_bitexact or two_column" 2>&1 | tail -5
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "sorted_execution or garbage or full_field_bitexact or two_column or c1_ or every_source" 2>&1 | tail -5
 for sort in 0 1; do
   XCAPE_B200_SORT=$sort python profiles/lab_time_kernel.py C2 2 10
   XCAPE_B200_SORT=$sort LAB_SHUFFLE=1 python profiles/lab_time_kernel.py C2 2 10

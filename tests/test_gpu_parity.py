@@ -176,7 +176,8 @@ def test_two_column_kernel_matches_one_column_kernel(core, cfg, vertical_lev, nc
 
 @pytest.mark.parametrize('cfg,vertical_lev,ncol', [('C1', 'sigma', 1000), ('C2', 'pressure', 8191), ('C2', 'pressure', 20001), ('C5', 'sigma', 1537)])
 @pytest.mark.parametrize('source', SOURCES)
-def test_sorted_execution_matches_storage_order(core, cfg, vertical_lev, ncol, source, monkeypatch):
+@pytest.mark.parametrize('mode', ['window', 'global'])
+def test_sorted_execution_matches_storage_order(core, cfg, vertical_lev, ncol, source, mode, monkeypatch):
     """Sorted execution of the faithful kernel (cape_sort.cuh: source parcels + keys, counting sort by (start level,
     theta-e), ascent in key order) only decides which columns share a warp: every output, status and iteration
     counter included, equals the storage-order run bit for bit — gated columns, odd column counts and the
@@ -191,6 +192,7 @@ def test_sorted_execution_matches_storage_order(core, cfg, vertical_lev, ncol, s
         p = d['p'] if p1d else d['p'].T
         return cape_cuda(p, d['t'].T, d['td'].T, d['ps'], d['ts'], d['tds'], 1 if p1d else 0, None, src, 500., adiabat, 500.,
                          2 if p1d else 1, return_counters=True)
+    monkeypatch.setenv('XCAPE_B200_SORT_MODE', mode)      # per-window bitonic sort / counting sort over the whole call
     for adiabat in (1, 2, 3, 4):
         monkeypatch.setenv('XCAPE_B200_SORT', '1')
         srt = run(adiabat)

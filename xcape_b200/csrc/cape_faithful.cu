@@ -66,21 +66,34 @@ static int launch(const CapeArgs& a, cudaStream_t s) {
     if (a.sort_scratch) {
       // sorted execution (cape_sort.cuh): source parcels + keys, per-window sort, then the ascent in key order
       SortBufs b = sort_carve(a.sort_scratch, a.ncol, a.nlev);
-      const char* tb = getenv("XCAPE_B200_SORT_TBIN");               // lab knob: theta-e bin width of the sort key, K
+      const char* tb = getenv("XCAPE_B200_SORT_TBIN");               // lab knob: theta-e bin width of the window key, K
       const float tbin = tb ? (float)atof(tb) : 4.0f;
       b.inv_tbin = 1.0f / (tbin > 0.01f ? tbin : 4.0f);
+      // global order (counting sort over the whole call) where the gathers it causes are cheap — a shared pressure
+      // axis (two gathered fields) of at most 64 levels; windows otherwise.  XCAPE_B200_SORT_MODE=window|global overrides.
+      const char* sm = getenv("XCAPE_B200_SORT_MODE");
+      const bool global_order = sm ? (sm[0] == 'g') : (P1D && a.nlev <= 64);
+      if (global_order) XC_CUDA(cudaMemsetAsync(b.hist, 0, sizeof(uint32_t) * (size_t)b.nbins_padded, s));
+      else b.hist = nullptr;
       cape_source_kernel<MathPolicy, SOURCE, P1D><<<(unsigned)((a.ncol + 127) / 128), 128, 0, s>>>(a, b);
       XC_LAUNCH_CHECK();
-      static std::once_flag smem_once[64];
-      int dev = 0;
-      XC_CUDA(cudaGetDevice(&dev));
-      cudaError_t attr_err = cudaSuccess;
-      std::call_once(smem_once[dev & 63], [&] {
-        attr_err = cudaFuncSetAttribute(cape_window_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortWindow * 8);
-      });
-      XC_CUDA(attr_err);
-      cape_window_sort_kernel<<<(unsigned)((a.ncol + kSortWindow - 1) / kSortWindow), kSortThreads, kSortWindow * 8, s>>>(b.key, b.perm, a.ncol);
-      XC_LAUNCH_CHECK();
+      if (global_order) {
+        cape_scan_kernel<<<1, 1024, 0, s>>>(b.hist, b.nbins_padded);
+        XC_LAUNCH_CHECK();
+        cape_scatter_kernel<<<(unsigned)((a.ncol + 255) / 256), 256, 0, s>>>(b.key, b.hist, b.perm, a.ncol);
+        XC_LAUNCH_CHECK();
+      } else {
+        static std::once_flag smem_once[64];
+        int dev = 0;
+        XC_CUDA(cudaGetDevice(&dev));
+        cudaError_t attr_err = cudaSuccess;
+        std::call_once(smem_once[dev & 63], [&] {
+          attr_err = cudaFuncSetAttribute(cape_window_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortWindow * 8);
+        });
+        XC_CUDA(attr_err);
+        cape_window_sort_kernel<<<(unsigned)((a.ncol + kSortWindow - 1) / kSortWindow), kSortThreads, kSortWindow * 8, s>>>(b.key, b.perm, a.ncol);
+        XC_LAUNCH_CHECK();
+      }
       CapeArgs as = a;
       as.sorted.perm = b.perm; as.sorted.rec_i = b.rec_i; as.sorted.rec_a = b.rec_a; as.sorted.rec_b = b.rec_b; as.sorted.rec_c = b.rec_c;
       cape_kernel2<MathPolicy, 1, ADIABAT, P1D, true><<<(unsigned)blocks2, threads2, 0, s>>>(as);

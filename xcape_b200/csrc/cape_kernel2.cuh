@@ -41,6 +41,12 @@ __device__ __forceinline__ f2 vfma(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c
 __device__ __forceinline__ f2 sadd(f2 a, f2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
 __device__ __forceinline__ f2 sadd(f2 a, float b) { return make_float2(__fadd_rn(a.x, b), __fadd_rn(a.y, b)); }
 __device__ __forceinline__ f2 ssub(f2 a, f2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+// The packed form of such an add: fma(a, 1, b) rounds a*1 + b = a + b once, i.e. IS the IEEE add, for one issue slot
+// instead of two scalar FADDs — provided the compiler cannot simplify it back into an add and contract that with the
+// multiply that produced `a`: the 1 is a kernel argument (CapeArgs::one), opaque at compile time.
+__device__ __forceinline__ f2 vaddx(f2 a, f2 b, float one) { return __ffma2_rn(a, splat(one), b); }
+__device__ __forceinline__ f2 vaddx(f2 a, float b, float one) { return __ffma2_rn(a, splat(one), splat(b)); }
+__device__ __forceinline__ f2 vsubx(f2 a, f2 b, float one) { return __ffma2_rn(b, splat(-one), a); }   // a - b
 __device__ __forceinline__ f2 vadd(f2 a, float b) { return __fadd2_rn(a, splat(b)); }
 __device__ __forceinline__ f2 vmul(f2 a, float b) { return __fmul2_rn(a, splat(b)); }
 __device__ __forceinline__ f2 vfma(f2 a, float b, float c) { return __ffma2_rn(a, splat(b), splat(c)); }
@@ -66,15 +72,28 @@ __device__ __forceinline__ f2 vexp32_core(f2 x) {
   f2 r = vfma(nf, -e32::kL1, x);
   r = vfma(nf, -e32::kL2, r);
   const int bx = __float_as_int(t.x), by = __float_as_int(t.y);
-  const int jx = bx & 1023, jy = by & 1023;
-  const f2 Th = make_float2(exp32_hi(jx), exp32_hi(jy)), Tl = make_float2(exp32_lo(jx), exp32_lo(jy));
+  // table addresses and exponent insertion in PTX: ptxas turns `and + mad.lo` into LOP3 + IMAD (two issue slots per
+  // half each), where the compiler's own canonical form (shift, mask, add) takes three
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sExp32);
+  unsigned ax, ay;
+  asm("{ .reg .b32 j; and.b32 j, %1, 1023; mad.lo.u32 %0, j, 4, %2; }" : "=r"(ax) : "r"(bx), "r"(sbase));
+  asm("{ .reg .b32 j; and.b32 j, %1, 1023; mad.lo.u32 %0, j, 4, %2; }" : "=r"(ay) : "r"(by), "r"(sbase));
+  f2 Th, Tl;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(Th.x) : "r"(ax));
+  asm("ld.shared.f32 %0, [%1];" : "=f"(Th.y) : "r"(ay));
+  asm("ld.shared.f32 %0, [%1+4096];" : "=f"(Tl.x) : "r"(ax));
+  asm("ld.shared.f32 %0, [%1+4096];" : "=f"(Tl.y) : "r"(ay));
   const f2 q = vfma(r, e32::kC3, 0.5f);
   const f2 v = vmul(r, r);
   const f2 p = vfma(q, v, r);
   const f2 y = vadd(Th, vfma(Th, p, Tl));
   f2 o;
-  o.x = __int_as_float((int)(((unsigned)(bx - 0x4B400000) >> 10) * 0x00800000u + (unsigned)__float_as_int(y.x)));
-  o.y = __int_as_float((int)(((unsigned)(by - 0x4B400000) >> 10) * 0x00800000u + (unsigned)__float_as_int(y.y)));
+  // exponent += n div 1024: bits(t) = 0x4B400000 + n and the low 19 bits of 0x4B400000 are zero, so
+  // ((n >> 10) << 23) == (bits(t) & ~1023) * 2^13 (mod 2^32)
+  unsigned ox, oy;
+  asm("{ .reg .b32 m; and.b32 m, %1, 0xFFFFFC00; mad.lo.u32 %0, m, 8192, %2; }" : "=r"(ox) : "r"(bx), "r"(__float_as_int(y.x)));
+  asm("{ .reg .b32 m; and.b32 m, %1, 0xFFFFFC00; mad.lo.u32 %0, m, 8192, %2; }" : "=r"(oy) : "r"(by), "r"(__float_as_int(y.y)));
+  o.x = __int_as_float((int)ox); o.y = __int_as_float((int)oy);
   return o;
 }
 // spec32_exp_tiny on both halves; |x| <= 2^-6
@@ -87,29 +106,29 @@ __device__ __forceinline__ f2 vexp32_tiny(f2 x) {
   u = vfma(u, x, 0.5f);
   return vadd(h, vfma(v, u, e));
 }
-__device__ __forceinline__ f2 vqsat(f2 p, f2 t, float a, float b) {   // getqvs / getqvi inside the window (f90:570-598)
+__device__ __forceinline__ f2 vqsat(f2 p, f2 t, float a, float b, float one) {   // getqvs / getqvi inside the window (f90:570-598)
   const f2 x = vdiv_fast(vmul(vadd(t, -273.15f), a), vadd(t, -b));
   const f2 es = vmul(vexp32_core(x), 611.2f);
-  return vdiv_fast(vmul(es, cc::eps_q), ssub(p, es));
+  return vdiv_fast(vmul(es, cc::eps_q), vsubx(p, es, one));
 }
 
 // moist_arg<M, ICE, true> of cape_kernel.cuh on both halves (same operations in the same order)
 template <bool ICE, bool PSEUDO>
-__device__ __forceinline__ f2 vmoist_arg(f2 t2, f2 p2, f2 qt, f2 t1, f2 qv1, f2 ql1, f2 qi1, f2 logp, f2& qv2, f2& ql2, f2& qi2) {
+__device__ __forceinline__ f2 vmoist_arg(f2 t2, f2 p2, f2 qt, f2 t1, f2 qv1, f2 ql1, f2 qi1, f2 logp, f2& qv2, f2& ql2, f2& qi2, float one) {
   f2 fice;
   if (ICE) {
     f2 fl = vdiv_fast(vadd(t2, -233.15f), splat(273.15f - 233.15f));
     fl.x = fmaxf(fminf(fl.x, 1.0f), 0.0f);
     fl.y = fmaxf(fminf(fl.y, 1.0f), 0.0f);
     fice = vsub(splat(1.0f), fl);
-    const f2 qs = sadd(vmul(fl, vqsat(p2, t2, 17.67f, 29.65f)), vmul(fice, vqsat(p2, t2, 21.8745584f, 7.66f)));
+    const f2 qs = vaddx(vmul(fl, vqsat(p2, t2, 17.67f, 29.65f, one)), vmul(fice, vqsat(p2, t2, 21.8745584f, 7.66f, one)), one);
     qv2 = make_float2(fminf(qt.x, qs.x), fminf(qt.y, qs.y));
     f2 w = vmul(fice, vsub(qt, qv2));
     qi2 = make_float2(fmaxf(w.x, 0.0f), fmaxf(w.y, 0.0f));
     w = vsub(vsub(qt, qv2), qi2);
     ql2 = make_float2(fmaxf(w.x, 0.0f), fmaxf(w.y, 0.0f));
   } else {
-    const f2 qs = vqsat(p2, t2, 17.67f, 29.65f);
+    const f2 qs = vqsat(p2, t2, 17.67f, 29.65f, one);
     qv2 = make_float2(fminf(qt.x, qs.x), fminf(qt.y, qs.y));
     qi2 = splat(0.0f);
     const f2 w = vsub(qt, qv2);
@@ -123,22 +142,22 @@ __device__ __forceinline__ f2 vmoist_arg(f2 t2, f2 p2, f2 qt, f2 t1, f2 qv1, f2 
   const f2 st = vadd(t1, t2);
   const f2 sq = vadd(qv1, qv2);
   const f2 sl = PSEUDO ? ql2 : vadd(ql1, ql2);                                 // ql1 = 0: 0 + x = x
-  const f2 lhv2 = sadd(vmul(st, -cc::lv2), 2.0f * cc::lv1);                    // 2 (lv1 - lv2*tbar)
-  const f2 rm = sadd(vmul(sq, 0.5f * cc::rv), cc::rd);
-  f2 cpm = sadd(sadd(vmul(sq, 0.5f * cc::cpv), cc::cp), vmul(sl, 0.5f * cc::cpl));
+  const f2 lhv2 = vaddx(vmul(st, -cc::lv2), 2.0f * cc::lv1, one);              // 2 (lv1 - lv2*tbar)
+  const f2 rm = vaddx(vmul(sq, 0.5f * cc::rv), cc::rd, one);
+  f2 cpm = vaddx(vmul(sl, 0.5f * cc::cpl), vaddx(vmul(sq, 0.5f * cc::cpv), cc::cp, one), one);   // (cp + cpv qvbar) + cpl qlbar
   const f2 dql = PSEUDO ? ql2 : vsub(ql2, ql1);
   f2 arg;
   if (ICE) {
     const f2 si = PSEUDO ? qi2 : vadd(qi1, qi2);
-    const f2 lhs2 = sadd(vmul(st, -cc::ls2), 2.0f * cc::ls1);
-    cpm = sadd(cpm, vmul(si, 0.5f * cc::cpi));
+    const f2 lhs2 = vaddx(vmul(st, -cc::ls2), 2.0f * cc::ls1, one);
+    cpm = vaddx(vmul(si, 0.5f * cc::cpi), cpm, one);
     const f2 den2 = vmul(cpm, st);                                             // 2 cpm tbar
     const f2 dqi = PSEUDO ? qi2 : vsub(qi2, qi1);
     arg = vadd(vdiv_fast(vmul(lhv2, dql), den2), vdiv_fast(vmul(lhs2, dqi), den2));
   } else {
     arg = vdiv_fast(vmul(lhv2, dql), vmul(cpm, st));
   }
-  return sadd(arg, vmul(vadd(vdiv_fast(rm, cpm), -cc::rddcp), logp));
+  return vaddx(vmul(vadd(vdiv_fast(rm, cpm), -cc::rddcp), logp), arg, one);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -237,22 +256,48 @@ __device__ __forceinline__ void col2_layer_begin(const CapeArgs& a, Col2& C, Lay
 }
 
 // sub-step prologue (f90:417-434): shift the state, step the pressure, Exner function and ln(p2/p1)
-template <class M, bool PSEUDO>
-__device__ __forceinline__ void col2_sub_begin(Col2& C, const Layer2& Y, Sub2& S) {
+template <bool PSEUDO>
+__device__ __forceinline__ void col2_sub_shift(Col2& C, const Layer2& Y, Sub2& S) {
   S.p1 = C.p2; S.t1 = C.t2; S.th1 = C.th2; S.qv1 = C.qv2;
   S.ql1 = PSEUDO ? 0.0f : C.ql2;                   // pseudo-adiabats reset condensate each sub-step (f90:487-491)
   S.qi1 = PSEUDO ? 0.0f : C.qi2;
   C.p2 = C.p2 - Y.dp;
+}
+__device__ __forceinline__ bool col2_window(const Col2& C, const Layer2& Y, const Sub2& S) {
+  return (Y.tmax >= 100.0f) && (S.t1 >= 90.0f) && (S.t1 <= 400.0f) && (C.qt == 0.0f || C.qt >= 1e-18f) && (C.qt <= 1.0f) &&
+         (S.ql1 <= 1.0f) && (S.qi1 <= 1.0f) && (fabsf(S.th1) < CUDART_INF_F);
+}
+template <class M, bool PSEUDO>
+__device__ __forceinline__ void col2_sub_begin(Col2& C, const Layer2& Y, Sub2& S) {
+  col2_sub_shift<PSEUDO>(C, Y, S);
   if (Y.fastp && C.p2 >= 2.0f) {
     // all operands normal and far from the range ends: the unguarded cores give what M::pow / M::log / `/` give
     C.pi2 = __double2float_rn(spec_exp_core(__dmul_rn((double)cc::rddcp, spec_log_core((double)(C.p2 * cc::rp00)))));
     S.logp = __double2float_rn(spec_log_core((double)fdiv_fast(C.p2, S.p1)));
-    S.window = (Y.tmax >= 100.0f) && (S.t1 >= 90.0f) && (S.t1 <= 400.0f) && (C.qt == 0.0f || C.qt >= 1e-18f) && (C.qt <= 1.0f) &&
-               (S.ql1 <= 1.0f) && (S.qi1 <= 1.0f) && (fabsf(S.th1) < CUDART_INF_F);
+    S.window = col2_window(C, Y, S);
   } else {
     C.pi2 = M::pow(C.p2 * cc::rp00, cc::rddcp);
     S.logp = M::log(C.p2 / S.p1);
     S.window = false;
+  }
+}
+// both columns of the thread at once: the four binary64 chains (two logs + one exp per column) are independent, and
+// written in one basic block they interleave — the FP64 pipe's latency, which a single chain exposes (ncu r2k: half of
+// the prologue's samples are fixed-latency waits), overlaps.  Same operations per column as col2_sub_begin.
+template <class M, bool PSEUDO>
+__device__ __forceinline__ void col2_sub_begin_pair(Col2& A, const Layer2& YA, Sub2& SA, Col2& B, const Layer2& YB, Sub2& SB) {
+  col2_sub_shift<PSEUDO>(A, YA, SA);
+  col2_sub_shift<PSEUDO>(B, YB, SB);
+  if (YA.fastp && A.p2 >= 2.0f && YB.fastp && B.p2 >= 2.0f) {
+    const double la = spec_log_core((double)(A.p2 * cc::rp00)), lb = spec_log_core((double)(B.p2 * cc::rp00));
+    const double ga = spec_log_core((double)fdiv_fast(A.p2, SA.p1)), gb = spec_log_core((double)fdiv_fast(B.p2, SB.p1));
+    const double ea = spec_exp_core(__dmul_rn((double)cc::rddcp, la)), eb = spec_exp_core(__dmul_rn((double)cc::rddcp, lb));
+    A.pi2 = __double2float_rn(ea); B.pi2 = __double2float_rn(eb);
+    SA.logp = __double2float_rn(ga); SB.logp = __double2float_rn(gb);
+    SA.window = col2_window(A, YA, SA); SB.window = col2_window(B, YB, SB);
+  } else {
+    A.pi2 = M::pow(A.p2 * cc::rp00, cc::rddcp); SA.logp = M::log(A.p2 / SA.p1); SA.window = false;
+    B.pi2 = M::pow(B.p2 * cc::rp00, cc::rddcp); SB.logp = M::log(B.p2 / SB.p1); SB.window = false;
   }
 }
 
@@ -373,8 +418,9 @@ __global__ void __launch_bounds__(XC_CAPE2_THREADS, XC_CAPE2_MIN_BLOCKS) cape_ke
       if (!(doA || doB)) break;
       Sub2 SA, SB;
       SA.window = false; SB.window = false;
-      if (doA) col2_sub_begin<M, PSEUDO>(A, YA, SA);
-      if (doB) col2_sub_begin<M, PSEUDO>(B, YB, SB);
+      if (doA && doB) col2_sub_begin_pair<M, PSEUDO>(A, YA, SA, B, YB, SB);
+      else if (doA) col2_sub_begin<M, PSEUDO>(A, YA, SA);
+      else col2_sub_begin<M, PSEUDO>(B, YB, SB);
       bool genA = doA, genB = doB;
       int iA = 0, iB = 0;
 
@@ -394,6 +440,7 @@ __global__ void __launch_bounds__(XC_CAPE2_THREADS, XC_CAPE2_MIN_BLOCKS) cape_ke
         // the window's accumulators are shared by the two halves (leaving it is rare, and the general loop is always right):
         // 90 <= every t2 <= the smaller tmax, every |arg| <= 2^-6
         const float tmx = fminf(wa ? YA.tmax : YB.tmax, wb ? YB.tmax : YA.tmax);
+        const float one = a.one;
         f2 thlast = th1;
         float t_hi = 90.0f, t_lo = 400.0f, a_hi = 0.0f;
         f2 t2, th2, qv2, ql2, qi2;
@@ -403,10 +450,10 @@ __global__ void __launch_bounds__(XC_CAPE2_THREADS, XC_CAPE2_MIN_BLOCKS) cape_ke
         do {
           t2 = vmul(thlast, pi2);
           t_hi = fmaxf(t_hi, fmaxf(t2.x, t2.y)); t_lo = fminf(t_lo, fminf(t2.x, t2.y));      // FMNMX3
-          const f2 arg = vmoist_arg<ICE, PSEUDO>(t2, p2, qt, t1, qv1, ql1, qi1, logp, qv2, ql2, qi2);
+          const f2 arg = vmoist_arg<ICE, PSEUDO>(t2, p2, qt, t1, qv1, ql1, qi1, logp, qv2, ql2, qi2, one);
           a_hi = fmaxf(a_hi, fmaxf(fabsf(arg.x), fabsf(arg.y)));
           th2 = vmul(th1, vexp32_tiny(arg));
-          const f2 d = ssub(th2, thlast);
+          const f2 d = vsubx(th2, thlast, one);
           const f2 step = vmul(d, 0.3f);
           mx = fabsf(d.x) > cc::converge; my = fabsf(d.y) > cc::converge;
           // a half that has converged keeps its thlast: the following passes recompute its final pass unchanged

@@ -31,18 +31,25 @@ namespace xc {
 constexpr int kSortWindow = 16384;             // columns per window: 128 KB of shared memory for the 64-bit sort elements
 constexpr int kSortThreads = 1024;
 
+constexpr int kSortThetaBins = 4096;           // global mode: 0.1 K bins of theta-e over [200, 609.6) K
+constexpr int kSortScanTile = 4096;            // bins per scan tile (1024 threads x int4)
+
 struct SortBufs {
   int4* rec_i; float4* rec_a; float4* rec_b; float2* rec_c;
   uint32_t* key; int32_t* perm;
-  float inv_tbin;                               // 1 / (theta-e bin width, K)
+  float inv_tbin;                               // window mode: 1 / (theta-e bin width, K)
+  uint32_t* hist;                               // global mode (counting sort over the whole call), else nullptr
+  int nbins, nbins_padded;                      // nlev * kSortThetaBins + 1 (last bin: no ascent), padded to the scan tile
 };
+inline int sort_nbins(int nlev) { return nlev * kSortThetaBins + 1; }
+inline int sort_nbins_padded(int nlev) { return (sort_nbins(nlev) + kSortScanTile - 1) / kSortScanTile * kSortScanTile; }
 
 inline size_t sort_align(size_t x) { return (x + 255) & ~(size_t)255; }
-inline size_t sort_scratch_bytes(int64_t ncol, int /*nlev*/) {
+inline size_t sort_scratch_bytes(int64_t ncol, int nlev) {
   const size_t n = (size_t)ncol;
-  return sort_align(16 * n) * 3 + sort_align(8 * n) + sort_align(4 * n) * 2;
+  return sort_align(16 * n) * 3 + sort_align(8 * n) + sort_align(4 * n) * 2 + sort_align(4 * (size_t)sort_nbins_padded(nlev));
 }
-inline SortBufs sort_carve(void* blob, int64_t ncol, int /*nlev*/) {
+inline SortBufs sort_carve(void* blob, int64_t ncol, int nlev) {
   char* q = (char*)blob;
   const size_t n = (size_t)ncol;
   SortBufs b;
@@ -51,7 +58,10 @@ inline SortBufs sort_carve(void* blob, int64_t ncol, int /*nlev*/) {
   b.rec_b = (float4*)q; q += sort_align(16 * n);
   b.rec_c = (float2*)q; q += sort_align(8 * n);
   b.key = (uint32_t*)q; q += sort_align(4 * n);
-  b.perm = (int32_t*)q;
+  b.perm = (int32_t*)q; q += sort_align(4 * n);
+  b.hist = (uint32_t*)q;
+  b.nbins = sort_nbins(nlev); b.nbins_padded = sort_nbins_padded(nlev);
+  b.inv_tbin = 0.25f;
   return b;
 }
 
@@ -78,6 +88,17 @@ __global__ void __launch_bounds__(128) cape_source_kernel(const CapeArgs a, cons
   b.rec_a[c] = make_float4(C.th2, C.pi2, C.p2, C.t2);
   b.rec_b[c] = make_float4(C.qv2, C.b2, C.z, C.prev_p);
   b.rec_c[c] = make_float2(C.prev_pi, C.prev_thv);
+  if (b.hist) {                                  // global mode: key = histogram bin (start level, theta-e in 0.1 K bins)
+    uint32_t bin = (uint32_t)(b.nbins - 1);
+    if (C.active) {
+      const float x = (thetae_key(C.p2, C.t2, C.qv2) - 200.0f) * 10.0f;
+      const int tb = (int)fminf(fmaxf(x, 0.0f), (float)(kSortThetaBins - 1));
+      bin = (uint32_t)(min(max(C.lev_next, 0), a.nlev - 1) * kSortThetaBins + tb);
+    }
+    b.key[c] = bin;
+    atomicAdd(b.hist + bin, 1u);
+    return;
+  }
   uint32_t key = 0xFFFFFFFFu;
   if (C.active) {
     const float x = (thetae_key(C.p2, C.t2, C.qv2) - 200.0f) * b.inv_tbin;
@@ -88,6 +109,51 @@ __global__ void __launch_bounds__(128) cape_source_kernel(const CapeArgs a, cons
     if (key == 0xFFFFFFFFu) key = 0xFFFFFFFEu;
   }
   b.key[c] = key;
+}
+
+// global mode: exclusive prefix sum of hist[0 .. nbins_padded) in place; one CTA of 1024 threads, 4 bins per thread per tile
+__global__ void __launch_bounds__(1024) cape_scan_kernel(uint32_t* __restrict__ hist, int nbins_padded) {
+  __shared__ uint32_t warp_sum[32];
+  __shared__ uint32_t carry_s;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nbins_padded; base += kSortScanTile) {
+    const uint4 v = reinterpret_cast<const uint4*>(hist + base)[threadIdx.x];
+    const uint32_t s1 = v.x, s2 = s1 + v.y, s3 = s2 + v.z, s4 = s3 + v.w;
+    uint32_t incl = s4;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_sum[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      const uint32_t ws = warp_sum[lane];
+      uint32_t wi = ws;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= d) wi += o;
+      }
+      warp_sum[lane] = wi - ws;                 // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    const uint32_t excl = carry_s + warp_sum[w] + (incl - s4);
+    reinterpret_cast<uint4*>(hist + base)[threadIdx.x] = make_uint4(excl, excl + s1, excl + s2, excl + s3);
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = excl + s4;
+    __syncthreads();
+  }
+}
+// global mode: counting-sort scatter.  Positions inside a bin follow the order of the atomics and may differ from run
+// to run — grouping (and therefore timing) only, never a result.
+__global__ void __launch_bounds__(256) cape_scatter_kernel(const uint32_t* __restrict__ key, uint32_t* __restrict__ cursor,
+                                                           int32_t* __restrict__ perm, int64_t ncol) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncol) return;
+  perm[atomicAdd(cursor + key[c], 1u)] = (int32_t)c;
 }
 
 // one CTA sorts one window: elements (key << 32 | index in window), bitonic network in shared memory

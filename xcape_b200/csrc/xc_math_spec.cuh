@@ -338,19 +338,19 @@ constexpr float kC3 = 0x1.555556p-3f;      // RN32(1/6)
 // LDS with a scaled index costs two instructions where the global-memory path costs five (64-bit address
 // arithmetic) plus an L1 round trip.  A kernel that uses the exp32 functions calls exp32_smem_fill() first.
 #ifndef XC_EXP32_GLOBAL_TABLE
-__shared__ float sExp32Hi[1024];
-__shared__ float sExp32Lo[1024];
+// one array, hi parts in [0, 1024) and lo parts in [1024, 2048): one address computation serves both loads (the second
+// is the first plus an immediate offset), and the two-column kernel loads the four values of a pair straight into
+// the halves of two packed registers
+__shared__ float sExp32[2048];
 __device__ __forceinline__ void exp32_smem_fill() {
   for (int k = threadIdx.x; k < 1024; k += blockDim.x) {
     const float2 T = kExp32T[k];
-    sExp32Hi[k] = T.x; sExp32Lo[k] = T.y;
+    sExp32[k] = T.x; sExp32[1024 + k] = T.y;
   }
   __syncthreads();
 }
-// hi and lo parts live in separate arrays so that the two-column kernel can load the four values of a pair
-// straight into the halves of two packed registers
-__device__ __forceinline__ float exp32_hi(int j) { return sExp32Hi[j]; }
-__device__ __forceinline__ float exp32_lo(int j) { return sExp32Lo[j]; }
+__device__ __forceinline__ float exp32_hi(int j) { return sExp32[j]; }
+__device__ __forceinline__ float exp32_lo(int j) { return sExp32[1024 + j]; }
 #else
 __device__ __forceinline__ void exp32_smem_fill() {}
 __device__ __forceinline__ float exp32_hi(int j) { return __ldg(&kExp32T[j].x); }
