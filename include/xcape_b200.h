@@ -182,6 +182,14 @@ XCAPE_API int xcape_cuda_measure_peaks(int device, int reps, double* fp32_tflops
  * rate the register file lets a real kernel sustain — ~0.70 of the figure above on B200.  Reported beside it. */
 XCAPE_API int xcape_cuda_measure_fp32_rrr(int device, int reps, double* fp32_tflops);
 
+/* Device time of the DOMINANT kernel of a call, for roofline accounting (bench.py): after xcape_cuda_time_kernels(1)
+ * the calling thread's device-pointer calls record a CUDA event pair on their stream around the column kernel alone
+ * (the CAPE ascent kernel, without the source-parcel / ordering kernels of its sorted execution; the streaming SRH
+ * kernel); xcape_cuda_last_kernel_ms waits for the pair recorded last by this thread and returns the elapsed
+ * milliseconds.  Off by default (no events are recorded). */
+XCAPE_API int xcape_cuda_time_kernels(int enable);
+XCAPE_API int xcape_cuda_last_kernel_ms(double* ms);
+
 #ifdef __cplusplus
 }
 #endif

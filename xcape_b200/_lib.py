@@ -22,7 +22,8 @@ OK, ERR_ARG, ERR_CUDA, ERR_NODEV = 0, 1, 2, 3
 SYMBOLS = ('xcape_cuda_cape', 'xcape_cuda_srh', 'xcape_cuda_srh_from_heights', 'xcape_cuda_stdheight', 'xcape_cuda_pres_lev_pos',
            'xcape_cuda_last_error', 'xcape_cuda_device_count', 'xcape_cuda_version',
            'xcape_cuda_kernel_launches', 'xcape_cuda_measure_peaks', 'xcape_cuda_release_memory',
-           'xcape_cuda_dewpoint_from_q', 'xcape_cuda_columns_redone', 'xcape_cuda_measure_fp32_rrr')
+           'xcape_cuda_dewpoint_from_q', 'xcape_cuda_columns_redone', 'xcape_cuda_measure_fp32_rrr',
+           'xcape_cuda_time_kernels', 'xcape_cuda_last_kernel_ms')
 
 _lib = None
 
@@ -72,6 +73,10 @@ def lib():
         L.xcape_cuda_measure_peaks.argtypes = [i32, i32, C.POINTER(f64), C.POINTER(f64)]
         L.xcape_cuda_measure_fp32_rrr.restype = i32
         L.xcape_cuda_measure_fp32_rrr.argtypes = [i32, i32, C.POINTER(f64)]
+        L.xcape_cuda_time_kernels.restype = i32
+        L.xcape_cuda_time_kernels.argtypes = [i32]
+        L.xcape_cuda_last_kernel_ms.restype = i32
+        L.xcape_cuda_last_kernel_ms.argtypes = [C.POINTER(f64)]
         _lib = L
     return _lib
 
@@ -104,6 +109,18 @@ def measure_fp32_rrr(device=0, reps=5):
     """FFMA TFLOP/s with three distinct register operands per instruction (what the register file sustains)."""
     a = C.c_double(0.0)
     check(lib().xcape_cuda_measure_fp32_rrr(int(device), int(reps), C.byref(a)))
+    return a.value
+
+
+def time_kernels(enable=True):
+    """Record a CUDA event pair around the dominant column kernel of this thread's device-pointer calls."""
+    check(lib().xcape_cuda_time_kernels(1 if enable else 0))
+
+
+def last_kernel_ms():
+    """Device milliseconds of the dominant kernel of this thread's last timed call (waits for it)."""
+    a = C.c_double(0.0)
+    check(lib().xcape_cuda_last_kernel_ms(C.byref(a)))
     return a.value
 
 

@@ -20,6 +20,26 @@ namespace xc {
 
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
+// per-thread event pair of xcape_cuda_time_kernels (events belong to the device they were created on)
+thread_local bool t_time_kernels = false, t_timer_valid = false;
+thread_local cudaEvent_t t_timer_ev[2] = {nullptr, nullptr};
+thread_local int t_timer_dev = -1;
+void kernel_timer_begin(cudaStream_t s) {
+  if (!t_time_kernels) return;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  if (t_timer_dev != dev) {
+    for (auto& e : t_timer_ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+    if (cudaEventCreate(&t_timer_ev[0]) != cudaSuccess || cudaEventCreate(&t_timer_ev[1]) != cudaSuccess) { t_timer_dev = -1; return; }
+    t_timer_dev = dev;
+  }
+  t_timer_valid = false;
+  cudaEventRecord(t_timer_ev[0], s);
+}
+void kernel_timer_end(cudaStream_t s) {
+  if (!t_time_kernels || t_timer_dev < 0) return;
+  t_timer_valid = cudaEventRecord(t_timer_ev[1], s) == cudaSuccess;
+}
 std::atomic<int64_t> g_redone{0};       // columns the host path handed back for a second pass with all levels
 
 namespace {
@@ -700,6 +720,18 @@ extern "C" {
 const char* xcape_cuda_last_error(void) { return g_last_error.c_str(); }
 const char* xcape_cuda_version(void) { return "xcape_b200 0.1.0 sm_100a"; }
 int64_t xcape_cuda_kernel_launches(void) { return g_launches.load(); }
+int xcape_cuda_time_kernels(int enable) { xc::t_time_kernels = enable != 0; return XCAPE_OK; }
+int xcape_cuda_last_kernel_ms(double* ms) {
+  using namespace xc;
+  if (!ms) return fail(XCAPE_ERR_ARG, "null pointer");
+  if (!t_timer_valid) return fail(XCAPE_ERR_ARG, "no timed kernel on this thread (call xcape_cuda_time_kernels(1) first)");
+  DeviceGuard dg(t_timer_dev);
+  XC_CUDA(cudaEventSynchronize(t_timer_ev[1]));
+  float f = 0.0f;
+  XC_CUDA(cudaEventElapsedTime(&f, t_timer_ev[0], t_timer_ev[1]));
+  *ms = (double)f;
+  return XCAPE_OK;
+}
 int64_t xcape_cuda_columns_redone(void) { return g_redone.load(); }
 int xcape_cuda_device_count(void) {
   int n = 0;

@@ -96,11 +96,15 @@ static int launch(const CapeArgs& a, cudaStream_t s) {
       }
       CapeArgs as = a;
       as.sorted.perm = b.perm; as.sorted.rec_i = b.rec_i; as.sorted.rec_a = b.rec_a; as.sorted.rec_b = b.rec_b; as.sorted.rec_c = b.rec_c;
+      kernel_timer_begin(s);
       cape_kernel2<MathPolicy, 1, ADIABAT, P1D, true><<<(unsigned)blocks2, threads2, 0, s>>>(as);
+      kernel_timer_end(s);
       XC_LAUNCH_CHECK();
       return XCAPE_OK;
     }
+    kernel_timer_begin(s);
     cape_kernel2<MathPolicy, SOURCE, ADIABAT, P1D, false><<<(unsigned)blocks2, threads2, 0, s>>>(a);
+    kernel_timer_end(s);
     XC_LAUNCH_CHECK();
     return XCAPE_OK;
   }
@@ -108,7 +112,9 @@ static int launch(const CapeArgs& a, cudaStream_t s) {
   const int threads = XC_CAPE_THREADS;
   const int64_t blocks = (a.ncol + threads - 1) / threads;
   if (blocks <= 0) return XCAPE_OK;
+  kernel_timer_begin(s);
   cape_kernel<MathPolicy, SOURCE, ADIABAT, P1D><<<(unsigned)blocks, threads, 0, s>>>(a);
+  kernel_timer_end(s);
   XC_LAUNCH_CHECK();
   return XCAPE_OK;
 }

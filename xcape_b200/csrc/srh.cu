@@ -17,11 +17,13 @@ int launch_srh_t(const SrhArgs<T>& a, bool p1d, cudaStream_t s) {
   if (a.ncol >= (int64_t)1 << 31) return fail(XCAPE_ERR_ARG, "srh: more than 2^31-1 columns per call");
   XC_CUDA(cudaMemsetAsync(a.work_count, 0, sizeof(int), s));
   const bool fh = a.fast_heights != 0;
+  kernel_timer_begin(s);
   if (a.aglh) srh_kernel<T, false, true, false><<<blocks, 128, 0, s>>>(a);
   else if (p1d && fh) srh_kernel<T, true, false, true><<<blocks, 128, 0, s>>>(a);
   else if (p1d) srh_kernel<T, true, false, false><<<blocks, 128, 0, s>>>(a);
   else if (fh) srh_kernel<T, false, false, true><<<blocks, 128, 0, s>>>(a);
   else srh_kernel<T, false, false, false><<<blocks, 128, 0, s>>>(a);
+  kernel_timer_end(s);
   XC_LAUNCH_CHECK();
   const unsigned eb = (unsigned)std::min<int64_t>(blocks, 148 * 4);   // grid-stride over the (usually empty) work list
   if (a.aglh) srh_exact_kernel<T, false, true, false><<<eb, 128, 0, s>>>(a);
@@ -43,10 +45,12 @@ int launch_srh_tile_t(const SrhArgs<T>& a, bool p1d, cudaStream_t s) {
   const unsigned blocks = (unsigned)((a.ncol + kTileCols - 1) / kTileCols);
   XC_CUDA(cudaMemsetAsync(a.work_count, 0, sizeof(int), s));
   const bool fh = a.fast_heights != 0;
+  kernel_timer_begin(s);
   if (p1d && fh) srh_tile_kernel<T, true, true><<<blocks, kTileCols, 0, s>>>(a);
   else if (p1d) srh_tile_kernel<T, true, false><<<blocks, kTileCols, 0, s>>>(a);
   else if (fh) srh_tile_kernel<T, false, true><<<blocks, kTileCols, 0, s>>>(a);
   else srh_tile_kernel<T, false, false><<<blocks, kTileCols, 0, s>>>(a);
+  kernel_timer_end(s);
   XC_LAUNCH_CHECK();
   const unsigned eb = (unsigned)std::min<int64_t>(blocks, 148 * 4);
   if (p1d && fh) srh_exact_kernel<T, true, false, true><<<eb, 128, 0, s>>>(a);

@@ -35,6 +35,10 @@ inline int fail(int code, const std::string& msg) {
     }                                                                                      \
   } while (0)
 
+// event pair around the dominant kernel of a call (xcape_cuda_time_kernels / xcape_cuda_last_kernel_ms); no-ops when off
+void kernel_timer_begin(cudaStream_t s);
+void kernel_timer_end(cudaStream_t s);
+
 inline size_t esize(int dtype) { return dtype == XCAPE_F64 ? 8 : 4; }
 
 // entry points of the per-TU kernel launchers
