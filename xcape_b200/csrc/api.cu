@@ -172,7 +172,7 @@ int cape_device(const void* p, const void* t, const void* td, const void* ps, co
   Scratch sc(s);
   CapeArgs a{};
   a.more_levels = more_levels ? 1 : 0;
-  a.one = 1.0f;
+  a.one2 = make_float2(1.0f, 1.0f);
   int rc;
   int64_t ld = ncol, ldp = ncol;
   const float* q;

@@ -40,7 +40,7 @@ struct CapeArgs {
                                    // a column still ascending after the last one gets status 4 (internal) and is redone
   const float* __restrict__ pl_pi; // P1D only, nullable: Exner function of the nlev pressure levels, precomputed once per
                                    // call by exner_table_kernel with the same SPEC pow (bit-identical, saves a pow per level)
-  float one;                       // 1.0f, set by the launcher: a multiplier the compiler cannot see through (cape_kernel2.cuh, vaddx)
+  float2 one2;                     // {1.0f, 1.0f}, set by the launcher: a multiplier the compiler cannot see through (cape_kernel2.cuh, vaddx)
   void* sort_scratch;              // faithful kernel only, nullable: cape_sort_scratch_bytes() bytes -> sorted execution
   CapeSorted sorted;               // filled by the launcher from sort_scratch
 };

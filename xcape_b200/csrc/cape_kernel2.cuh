@@ -43,10 +43,10 @@ __device__ __forceinline__ f2 sadd(f2 a, float b) { return make_float2(__fadd_rn
 __device__ __forceinline__ f2 ssub(f2 a, f2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
 // The packed form of such an add: fma(a, 1, b) rounds a*1 + b = a + b once, i.e. IS the IEEE add, for one issue slot
 // instead of two scalar FADDs — provided the compiler cannot simplify it back into an add and contract that with the
-// multiply that produced `a`: the 1 is a kernel argument (CapeArgs::one), opaque at compile time.
-__device__ __forceinline__ f2 vaddx(f2 a, f2 b, float one) { return __ffma2_rn(a, splat(one), b); }
-__device__ __forceinline__ f2 vaddx(f2 a, float b, float one) { return __ffma2_rn(a, splat(one), splat(b)); }
-__device__ __forceinline__ f2 vsubx(f2 a, f2 b, float one) { return __ffma2_rn(b, splat(-one), a); }   // a - b
+// multiply that produced `a`: the 1 is a kernel argument (CapeArgs::one2), opaque at compile time.
+__device__ __forceinline__ f2 vaddx(f2 a, f2 b, f2 one) { return __ffma2_rn(a, one, b); }
+__device__ __forceinline__ f2 vaddx(f2 a, float b, f2 one) { return __ffma2_rn(a, one, splat(b)); }
+__device__ __forceinline__ f2 vsubx(f2 a, f2 b, f2 one) { return __ffma2_rn(b, vneg(one), a); }   // a - b
 __device__ __forceinline__ f2 vadd(f2 a, float b) { return __fadd2_rn(a, splat(b)); }
 __device__ __forceinline__ f2 vmul(f2 a, float b) { return __fmul2_rn(a, splat(b)); }
 __device__ __forceinline__ f2 vfma(f2 a, float b, float c) { return __ffma2_rn(a, splat(b), splat(c)); }
@@ -106,7 +106,7 @@ __device__ __forceinline__ f2 vexp32_tiny(f2 x) {
   u = vfma(u, x, 0.5f);
   return vadd(h, vfma(v, u, e));
 }
-__device__ __forceinline__ f2 vqsat(f2 p, f2 t, float a, float b, float one) {   // getqvs / getqvi inside the window (f90:570-598)
+__device__ __forceinline__ f2 vqsat(f2 p, f2 t, float a, float b, f2 one) {   // getqvs / getqvi inside the window (f90:570-598)
   const f2 x = vdiv_fast(vmul(vadd(t, -273.15f), a), vadd(t, -b));
   const f2 es = vmul(vexp32_core(x), 611.2f);
   return vdiv_fast(vmul(es, cc::eps_q), vsubx(p, es, one));
@@ -114,7 +114,7 @@ __device__ __forceinline__ f2 vqsat(f2 p, f2 t, float a, float b, float one) {  
 
 // moist_arg<M, ICE, true> of cape_kernel.cuh on both halves (same operations in the same order)
 template <bool ICE, bool PSEUDO>
-__device__ __forceinline__ f2 vmoist_arg(f2 t2, f2 p2, f2 qt, f2 t1, f2 qv1, f2 ql1, f2 qi1, f2 logp, f2& qv2, f2& ql2, f2& qi2, float one) {
+__device__ __forceinline__ f2 vmoist_arg(f2 t2, f2 p2, f2 qt, f2 t1, f2 qv1, f2 ql1, f2 qi1, f2 logp, f2& qv2, f2& ql2, f2& qi2, f2 one) {
   f2 fice;
   if (ICE) {
     f2 fl = vdiv_fast(vadd(t2, -233.15f), splat(273.15f - 233.15f));
@@ -380,8 +380,9 @@ __device__ __forceinline__ void col2_store(const CapeArgs& a, const Col2& C) {
 #define XC_CAPE2_THREADS 128
 #endif
 #ifndef XC_CAPE2_MIN_BLOCKS
-#define XC_CAPE2_MIN_BLOCKS 5    // <= 102 registers.  Measured per ERA5 field (ms): 4 CTAs 8.88, 5 CTAs 8.66, 6 CTAs 8.71, 3 x 256 threads 8.63:
-#endif                           // the kernel is bound by FMA-pipe / register-file bandwidth, not by occupancy
+#define XC_CAPE2_MIN_BLOCKS 5    // 96 registers.  Measured per ERA5 field, sorted execution (ms, whole call; profiles/r2l_lab_launch_geometry*.txt):
+#endif                           // 5 x 128 threads 7.58; 4 x 128 (128 regs, no spills) 7.93; 6 x 128 (80 regs) 7.80; 9 x 64 / 6 x 96 / 3 x 192 at
+                                 // 112 regs 7.73 / 8.06 / 8.58: bound by FMA-pipe throughput and issue, not by occupancy or the spills
 // SORTED: the columns come in the order a.sorted.perm with their source parcels in records (cape_sort.cuh); SOURCE is
 // then irrelevant (instantiated with 1 only)
 template <class M, int SOURCE, int ADIABAT, bool P1D, bool SORTED>
@@ -440,7 +441,7 @@ __global__ void __launch_bounds__(XC_CAPE2_THREADS, XC_CAPE2_MIN_BLOCKS) cape_ke
         // the window's accumulators are shared by the two halves (leaving it is rare, and the general loop is always right):
         // 90 <= every t2 <= the smaller tmax, every |arg| <= 2^-6
         const float tmx = fminf(wa ? YA.tmax : YB.tmax, wb ? YB.tmax : YA.tmax);
-        const float one = a.one;
+        const f2 one = a.one2;
         f2 thlast = th1;
         float t_hi = 90.0f, t_lo = 400.0f, a_hi = 0.0f;
         f2 t2, th2, qv2, ql2, qi2;
