@@ -19,7 +19,14 @@ namespace xc {
 
 constexpr int kTileCols = 128;
 
-template <class T> struct TileCfg { static constexpr int KC = (sizeof(T) == 4) ? 8 : 4; };   // 32-byte pieces
+#ifndef XC_SRH_TILE_KC
+#define XC_SRH_TILE_KC 4          // levels per chunk for 4-byte elements (16-byte pieces); half as many for 8-byte elements.  Measured per HRRR
+                                  // field (ms, device path; profiles/r2p_lab_srh_tile_geometry.txt): KC 8 x 5 CTAs 1.31, 4 x 5 0.94, 4 x 6 0.87, 4 x 7 0.90, 4 x 8 1.10, 2 x 8 1.03
+#endif
+#ifndef XC_SRH_TILE_MIN_BLOCKS
+#define XC_SRH_TILE_MIN_BLOCKS 6
+#endif
+template <class T> struct TileCfg { static constexpr int KC = (sizeof(T) == 4) ? XC_SRH_TILE_KC : XC_SRH_TILE_KC / 2; };
 constexpr int kTilePad = 4;           // row stride 132: the transposing stores of a warp hit 32 distinct banks
 
 // asynchronous copy (LDGSTS) of levels [k0, k0 + KC) of the tile's columns of one level-last field into s[kk][col];
@@ -44,7 +51,7 @@ __device__ __forceinline__ void tile_load_async(const T* __restrict__ g, int64_t
 // level-last SrhArgs: a.p/t/td/u/v point at [ncol][nlev] arrays (P1D: a.p is [nlev]); a.ld unused.
 // Two chunk buffers: the copies of chunk i+1 are in flight while chunk i is computed.
 template <class T, bool P1D, bool FH>
-__global__ void __launch_bounds__(kTileCols, 5) srh_tile_kernel(const SrhArgs<T> a) {
+__global__ void __launch_bounds__(kTileCols, XC_SRH_TILE_MIN_BLOCKS) srh_tile_kernel(const SrhArgs<T> a) {
   constexpr int KC = TileCfg<T>::KC;
   constexpr int W = kTileCols + kTilePad;
   __shared__ T sP[2][P1D ? 1 : KC][W];
