@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 {
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "srh or stdheight" 2>&1 | tail -2
+
 for lib in gpurun_lab/lib_kc*.so xcape_b200/libxcape_b200.so; do
   XCAPE_B200_LIB=$PWD/$lib python bench.py --workload C4 --no-extras --no-cpu-baseline --steps 10 --warmup 3 2>&1 | tail -1 | python -c "
 import sys, json

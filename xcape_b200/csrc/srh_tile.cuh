@@ -17,7 +17,10 @@
 
 namespace xc {
 
-constexpr int kTileCols = 128;
+#ifndef XC_SRH_TILE_COLS
+#define XC_SRH_TILE_COLS 128
+#endif
+constexpr int kTileCols = XC_SRH_TILE_COLS;
 
 #ifndef XC_SRH_TILE_KC
 #define XC_SRH_TILE_KC 4          // levels per chunk for 4-byte elements (16-byte pieces); half as many for 8-byte elements.  Measured per HRRR
