@@ -20,3 +20,14 @@ print('cpu', r['cpu_baseline'])
 PY
 } > gpurun_out/full_lab.txt 2>&1
 cat gpurun_out/full_lab.txt
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/final_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > /dev/null 2>&1
+python - <<'PY' >> gpurun_out/full_lab.txt
+import csv, collections
+rows = [r for r in csv.reader(open('gpurun_out/final_launches_bench.csv')) if len(r) > 10 and r[0].isdigit()]
+tot = collections.Counter(); n = collections.Counter()
+for r in rows:
+    name = r[4].split('(')[0][:70]; tot[name] += float(r[-1]); n[name] += 1
+s = sum(tot.values())
+for k, v in tot.most_common(12): print(f'{v / s * 100:6.2f} %  {n[k]:4d} x  {k}')
+PY
+tail -14 gpurun_out/full_lab.txt

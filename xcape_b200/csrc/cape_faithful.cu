@@ -78,7 +78,10 @@ static int launch(const CapeArgs& a, cudaStream_t s) {
       cape_source_kernel<MathPolicy, SOURCE, P1D><<<(unsigned)((a.ncol + 127) / 128), 128, 0, s>>>(a, b);
       XC_LAUNCH_CHECK();
       if (global_order) {
-        cape_scan_kernel<<<1, 1024, 0, s>>>(b.hist, b.nbins_padded);
+        const unsigned ntiles = (unsigned)(b.nbins_padded / kSortScanTile);
+        cape_scan_totals_kernel<<<ntiles, 1024, 0, s>>>(b.hist, b.tile_total);
+        XC_LAUNCH_CHECK();
+        cape_scan_kernel<<<ntiles, 1024, 0, s>>>(b.hist, b.tile_total);
         XC_LAUNCH_CHECK();
         cape_scatter_kernel<<<(unsigned)((a.ncol + 255) / 256), 256, 0, s>>>(b.key, b.hist, b.perm, a.ncol);
         XC_LAUNCH_CHECK();
