@@ -107,6 +107,19 @@ XCAPE_API int xcape_cuda_cape(const void* p, const void* t, const void* td,
                     float* cape, float* cin, int32_t* mulev, float* zmulev, int32_t* status,
                     int32_t* n_iter, int precision, int device, void* stream);
 
+/* xcape_cuda_cape on HOST memory over several GPUs of one box: [0, ncol) is split into contiguous blocks of whole
+ * 128-column units, one per entry of `devices` (an index may repeat), each block runs the host path of xcape_cuda_cape on
+ * its device from its own host thread; no collective, no peer traffic (columns are independent).  Replaces
+ * the chunk-level parallelism the reference gets from dask (core.py:237-258) for one in-memory field.  Returns the
+ * first failing device's code; outputs of the other blocks are complete. */
+XCAPE_API int xcape_cuda_cape_multi(const void* p, const void* t, const void* td,
+                    const void* ps, const void* ts, const void* tds,
+                    int64_t ncol, int nlev, int p_is_1d, int dtype, int layout,
+                    int source, int adiabat, float ml_depth, float pinc,
+                    const int32_t* start_3d,
+                    float* cape, float* cin, int32_t* mulev, float* zmulev, int32_t* status,
+                    int32_t* n_iter, int precision, const int* devices, int ndevices);
+
 /* ---------------------------------------------------------------------------------------
  * Storm-relative helicity, fused.  Replaces, in one pass over the column,
  *   loop_stdheight_ml / loop_stdheight_pl1d  (stdheight_2D_model_lev.pyf:6-19,
@@ -125,6 +138,14 @@ XCAPE_API int xcape_cuda_srh(const void* p, const void* t, const void* td, const
                    double depth, double aglh0, const int32_t* start_3d,
                    double* srh_rm, double* srh_lm, float* rm, float* lm, float* mean6,
                    int precision, int device, void* stream);
+
+/* xcape_cuda_srh on HOST memory over several GPUs of one box (see xcape_cuda_cape_multi). */
+XCAPE_API int xcape_cuda_srh_multi(const void* p, const void* t, const void* td, const void* u, const void* v,
+                   const void* ps, const void* ts, const void* tds, const void* us, const void* vs,
+                   int64_t ncol, int nlev, int p_is_1d, int dtype, int layout,
+                   double depth, double aglh0, const int32_t* start_3d,
+                   double* srh_rm, double* srh_lm, float* rm, float* lm, float* mean6,
+                   int precision, const int* devices, int ndevices);
 
 /* The reference's two-call form: heights already computed (by xcape_cuda_stdheight or by the
  * caller).  Replaces bunkers_loop_ml / bunkers_loop_pl + loop_sreh_ml / loop_sreh_pl exactly as

@@ -680,6 +680,46 @@ def test_devices_kwarg_shards_columns_over_gpus(core):
     assert_bitexact(lm, one, 'level-major sharded')
 
 
+@pytest.mark.parametrize('cfg,vertical_lev', [('C2', 'pressure'), ('C3', 'sigma')])
+@pytest.mark.parametrize('lev_axis', [-1, 0])
+def test_cape_multi_entry_shards_on_one_gpu(core, cfg, vertical_lev, lev_axis):
+    """xcape_cuda_cape_multi (one C call, one host thread per entry of `devices`) with the SAME device listed three
+    times, so that the sharding arithmetic — block boundaries, a level-major shard addressed through the field's pitch,
+    the level window with its redo pass per shard, status / counter outputs — runs on a one-GPU box too.  Results equal
+    the single-device call bit for bit."""
+    from xcape_b200.cape_cuda import cape as cape_cuda
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings(cfg, cols=(0, 70_000 + 13), active=False)
+    p1d = d['p'].ndim == 1
+    # a few columns that are still buoyant at 100 hPa: the level window has to redo them with every level
+    if p1d:
+        d['t'][::997, 20:] += 25.0
+    kw = dict(source='most-unstable', pinc=500., vertical_lev=vertical_lev, method='cuda', lev_axis=lev_axis)
+    t, td = (d['t'], d['td']) if lev_axis == -1 else (np.ascontiguousarray(d['t'].T), np.ascontiguousarray(d['td'].T))
+    p = d['p'] if p1d else (d['p'] if lev_axis == -1 else np.ascontiguousarray(d['p'].T))
+    one = core.calc_cape(p, t, td, d['ps'], d['ts'], d['tds'], **kw)
+    many = core.calc_cape(p, t, td, d['ps'], d['ts'], d['tds'], devices=[0, 0, 0], **kw)
+    assert_bitexact(many, one, f'{cfg} lev_axis={lev_axis} devices=[0, 0, 0]')
+    pm = d['p'] if p1d else d['p'].T
+    c1 = cape_cuda(pm, d['t'].T, d['td'].T, d['ps'], d['ts'], d['tds'], 1 if p1d else 0, None, 2, 500., 1, 500., 2 if p1d else 1,
+                   return_counters=True)
+    c3 = cape_cuda(pm, d['t'].T, d['td'].T, d['ps'], d['ts'], d['tds'], 1 if p1d else 0, None, 2, 500., 1, 500., 2 if p1d else 1,
+                   return_counters=True, devices=[0, 0, 0])
+    for a, b, name in zip(c3, c1, ('cape', 'cin', 'mulev', 'zmulev', 'status', 'n_iter')):
+        assert np.array_equal(a, b), name
+    with pytest.raises(Exception):
+        core.calc_cape(p, t, td, d['ps'], d['ts'], d['tds'], devices=[0, 99], **kw)      # no such device: reported, not ignored
+    d4 = make_soundings('C4' if cfg == 'C3' else cfg, cols=(0, 40_000 + 7))
+    u, v = (d4['u'], d4['v']) if lev_axis == -1 else (np.ascontiguousarray(d4['u'].T), np.ascontiguousarray(d4['v'].T))
+    t4, td4 = (d4['t'], d4['td']) if lev_axis == -1 else (np.ascontiguousarray(d4['t'].T), np.ascontiguousarray(d4['td'].T))
+    p4 = d4['p'] if p1d else (d4['p'] if lev_axis == -1 else np.ascontiguousarray(d4['p'].T))
+    skw = dict(depth=3000, vertical_lev=vertical_lev, output_var='all', method='cuda', lev_axis=lev_axis)
+    s1 = core.calc_srh(p4, t4, td4, u, v, d4['ps'], d4['ts'], d4['tds'], d4['us'], d4['vs'], **skw)
+    s3 = core.calc_srh(p4, t4, td4, u, v, d4['ps'], d4['ts'], d4['tds'], d4['us'], d4['vs'], devices=[0, 0, 0], **skw)
+    for a, b in zip(s3, s1):
+        assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize('precision', ['fast', 'fast-relaxed'])
 @pytest.mark.parametrize('adiabat', ADIABATS)
 @pytest.mark.parametrize('source', ['surface', 'most-unstable'])

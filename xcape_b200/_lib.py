@@ -19,7 +19,7 @@ PRECISION = {'faithful': FAITHFUL, 'fast': FAST, 'fast-relaxed': FAST_RELAXED, '
 OK, ERR_ARG, ERR_CUDA, ERR_NODEV = 0, 1, 2, 3
 
 # every symbol include/xcape_b200.h declares (tests check the library exports all of them)
-SYMBOLS = ('xcape_cuda_cape', 'xcape_cuda_srh', 'xcape_cuda_srh_from_heights', 'xcape_cuda_stdheight', 'xcape_cuda_pres_lev_pos',
+SYMBOLS = ('xcape_cuda_cape', 'xcape_cuda_cape_multi', 'xcape_cuda_srh', 'xcape_cuda_srh_multi', 'xcape_cuda_srh_from_heights', 'xcape_cuda_stdheight', 'xcape_cuda_pres_lev_pos',
            'xcape_cuda_last_error', 'xcape_cuda_device_count', 'xcape_cuda_version',
            'xcape_cuda_kernel_launches', 'xcape_cuda_measure_peaks', 'xcape_cuda_release_memory',
            'xcape_cuda_dewpoint_from_q', 'xcape_cuda_columns_redone', 'xcape_cuda_measure_fp32_rrr',
@@ -51,9 +51,15 @@ def lib():
         L.xcape_cuda_cape.restype = i32
         L.xcape_cuda_cape.argtypes = [vp] * 6 + [i64, i32, i32, i32, i32, i32, i32, i32, f32, f32, vp,
                                                vp, vp, vp, vp, vp, vp, i32, i32, vp]
+        L.xcape_cuda_cape_multi.restype = i32
+        L.xcape_cuda_cape_multi.argtypes = [vp] * 6 + [i64, i32, i32, i32, i32, i32, i32, f32, f32, vp,
+                                                     vp, vp, vp, vp, vp, vp, i32, C.POINTER(i32), i32]
         L.xcape_cuda_srh.restype = i32
         L.xcape_cuda_srh.argtypes = [vp] * 10 + [i64, i32, i32, i32, i32, i32, f64, f64, vp,
                                                vp, vp, vp, vp, vp, i32, i32, vp]
+        L.xcape_cuda_srh_multi.restype = i32
+        L.xcape_cuda_srh_multi.argtypes = [vp] * 10 + [i64, i32, i32, i32, i32, f64, f64, vp,
+                                                     vp, vp, vp, vp, vp, i32, C.POINTER(i32), i32]
         L.xcape_cuda_srh_from_heights.restype = i32
         L.xcape_cuda_srh_from_heights.argtypes = [vp] * 6 + [i64, i32, i32, i32, i32, f64, vp, vp, vp, vp, vp, vp, i32, vp]
         L.xcape_cuda_stdheight.restype = i32

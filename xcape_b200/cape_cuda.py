@@ -12,7 +12,6 @@ import numpy as np
 
 from . import _array as A
 from . import _lib
-from .sharding import column_blocks, run_on_devices
 
 
 def _wider_than_fields(one_d, fields):
@@ -131,8 +130,16 @@ def cape(p_2d, t_2d, td_2d, p_s, t_s, td_s, flag_1d, pres_lev_pos, source, ml_de
         _lib.check(rc)
 
     if mem == _lib.MEM_HOST and devices is not None and len(devices) > 1:
-        blocks = column_blocks(ngrid, len(devices))
-        run_on_devices(lambda b, d: call(b[0], b[1], d), blocks, list(devices))
+        # one C call: the library splits [0, ngrid) into contiguous 128-aligned blocks (the rule of
+        # sharding.column_blocks) and runs each block's host path on its device from its own host thread
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        rc = L.xcape_cuda_cape_multi(
+            A.ptr(p), A.ptr(t_), A.ptr(td_), A.ptr(ps_), A.ptr(ts_), A.ptr(tds_), C.c_int64(ngrid), nlev, p_is_1d, dt,
+            layout | (_lib.LEVELS_TOP_FIRST if top_first else 0), int(source), int(adiabat),
+            C.c_float(float(ml_depth)), C.c_float(float(pinc)), None if start is None else A.ptr(start),
+            A.ptr(cape_o), A.ptr(cin_o), A.ptr(mu_o), A.ptr(z_o), None if st_o is None else A.ptr(st_o),
+            None if it_o is None else A.ptr(it_o), prec, devs, len(devices))
+        _lib.check(rc)
     else:
         dev = A.device_of(ref, devices[0] if devices else device)
         call(0, ngrid, dev)

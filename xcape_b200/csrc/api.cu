@@ -529,8 +529,12 @@ RingPool g_rings;
 // callback then sees nl-level blocks.  Calls with 3-D outputs ship every level.
 template <class F>
 int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_host, const std::vector<HostIn3>& in3,
-               const std::vector<HostIn1>& in1, const std::vector<HostOut>& outs, F launch, int l0 = 0, int nl = -1) {
+               const std::vector<HostIn1>& in1, const std::vector<HostOut>& outs, F launch, int l0 = 0, int nl = -1,
+               int64_t pitch = -1, int64_t col0 = 0) {
+  // `pitch`, `col0`: the call works on columns [col0, col0 + ncol) of host arrays that hold `pitch` columns (a shard of a
+  // larger field, xcape_cuda_*_multi): every host address below is formed with col0 + c and, for level-major rows, pitch.
   if (nl < 0) nl = nlev;
+  if (pitch < 0) pitch = ncol;
   const int64_t chunk = std::min<int64_t>(ncol, chunk_cols());          // capacity of a slot
   const int64_t first = std::min<int64_t>(chunk, first_chunk_cols());
   // block plan: geometric ramp, then full blocks; a short remainder is shared with its predecessor so that
@@ -573,12 +577,12 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
     for (size_t k = 0; k < outs.size(); ++k) {
       if (!staged[k]) continue;
       const size_t bpc = outs[k].bytes_per_col;
-      const int64_t c0 = pend[i].c0, n = pend[i].n;
+      const int64_t c0 = pend[i].c0 + col0, n = pend[i].n;
       if (!outs[k].is3d) { memcpy((char*)outs[k].host + (size_t)c0 * bpc, stage[i][k], (size_t)n * bpc); continue; }
       // a 3-D field in the inputs' layout: the slot holds the dense [n][nlev] / [nlev][n] block
       if (layout == XCAPE_LEVEL_LAST) parallel_memcpy((char*)outs[k].host + (size_t)c0 * nlev * bpc, stage[i][k], (size_t)n * nlev * bpc);
       else parallel_parts(nlev, [&](int lev) {
-        memcpy((char*)outs[k].host + ((size_t)lev * ncol + c0) * bpc, (const char*)stage[i][k] + (size_t)lev * n * bpc, (size_t)n * bpc);
+        memcpy((char*)outs[k].host + ((size_t)lev * pitch + c0) * bpc, (const char*)stage[i][k] + (size_t)lev * n * bpc, (size_t)n * bpc);
       });
     }
     pend[i].on = false;
@@ -643,14 +647,14 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
       }
       for (size_t k = 0; k < in3.size(); ++k) {
         if (stage3[i][k]) {        // pageable: host threads fill the slot's pinned buffer, then a true async H2D
-          stage_field(stage3[i][k], in3[k].host, layout, ncol, nlev, c0, n, es, l0, nl);
+          stage_field(stage3[i][k], in3[k].host, layout, pitch, nlev, c0 + col0, n, es, l0, nl);
           XC_CUDA(cudaMemcpyAsync(b[i].in3[k], stage3[i][k], (size_t)n * nl * es, cudaMemcpyHostToDevice, s));
         } else {
-          XC_CUDA(h2d_field(b[i].in3[k], in3[k].host, layout, ncol, nlev, c0, n, es, s, l0, nl));
+          XC_CUDA(h2d_field(b[i].in3[k], in3[k].host, layout, pitch, nlev, c0 + col0, n, es, s, l0, nl));
         }
       }
       for (size_t k = 0; k < in1.size(); ++k) {
-        const void* src = (const char*)in1[k].host + (size_t)c0 * in1[k].es;
+        const void* src = (const char*)in1[k].host + (size_t)(c0 + col0) * in1[k].es;
         if (stage1[i][k]) { memcpy(stage1[i][k], src, (size_t)n * in1[k].es); src = stage1[i][k]; }
         XC_CUDA(cudaMemcpyAsync(b[i].in1[k], src, (size_t)n * in1[k].es, cudaMemcpyHostToDevice, s));
       }
@@ -660,9 +664,9 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
       for (size_t k = 0; k < outs.size(); ++k) {
         if (!outs[k].host) continue;
         if (outs[k].is3d && staged[k]) XC_CUDA(cudaMemcpyAsync(stage[i][k], b[i].out[k], (size_t)n * nlev * outs[k].bytes_per_col, cudaMemcpyDeviceToHost, s));
-        else if (outs[k].is3d) XC_CUDA(d2h_field(outs[k].host, b[i].out[k], layout, ncol, nlev, c0, n, outs[k].bytes_per_col, s));
+        else if (outs[k].is3d) XC_CUDA(d2h_field(outs[k].host, b[i].out[k], layout, pitch, nlev, c0 + col0, n, outs[k].bytes_per_col, s));
         else if (staged[k]) XC_CUDA(cudaMemcpyAsync(stage[i][k], b[i].out[k], (size_t)n * outs[k].bytes_per_col, cudaMemcpyDeviceToHost, s));
-        else XC_CUDA(cudaMemcpyAsync((char*)outs[k].host + (size_t)c0 * outs[k].bytes_per_col, b[i].out[k], (size_t)n * outs[k].bytes_per_col, cudaMemcpyDeviceToHost, s));
+        else XC_CUDA(cudaMemcpyAsync((char*)outs[k].host + (size_t)(c0 + col0) * outs[k].bytes_per_col, b[i].out[k], (size_t)n * outs[k].bytes_per_col, cudaMemcpyDeviceToHost, s));
       }
       if (trace) mark(&tl.back().e[3], s);
       XC_CUDA(cudaEventRecord(done[i], s));
@@ -714,6 +718,35 @@ int run_staged(int64_t ncol, int nlev, int layout, size_t es, const void* p1d_ho
 }  // namespace xc
 
 using namespace xc;
+
+// block r of `ndevices` contiguous blocks of whole 128-column units (xcape_b200/sharding.py::column_blocks)
+static void shard_block(int64_t ncol, int ndevices, int r, int64_t* c0, int64_t* c1) {
+  const int64_t units = (ncol + 127) / 128, base = units / ndevices, extra = units % ndevices;
+  const int64_t u0 = (int64_t)r * base + std::min<int64_t>(r, extra), u1 = u0 + base + (r < extra ? 1 : 0);
+  *c0 = std::min(u0 * 128, ncol); *c1 = std::min(u1 * 128, ncol);
+}
+// fn(r, c0, c1) on one host thread per non-empty block, each bound to its device; first failure wins
+template <class F>
+static int run_sharded(int64_t ncol, const int* devices, int ndevices, F fn) {
+  std::vector<int> rcs((size_t)ndevices, XCAPE_OK);
+  std::vector<std::string> msgs((size_t)ndevices);
+  std::vector<std::thread> th;
+  for (int r = 0; r < ndevices; ++r) {
+    int64_t c0, c1;
+    shard_block(ncol, ndevices, r, &c0, &c1);
+    if (c1 <= c0) continue;
+    th.emplace_back([&, r, c0, c1] {
+      DeviceGuard dg(devices[r]);
+      if (!dg.ok) { rcs[(size_t)r] = XCAPE_ERR_NODEV; msgs[(size_t)r] = "cudaSetDevice failed"; return; }
+      rcs[(size_t)r] = fn(r, c0, c1);
+      if (rcs[(size_t)r]) msgs[(size_t)r] = g_last_error;      // thread-local: carry it to the caller's thread
+    });
+  }
+  for (auto& x : th) x.join();
+  for (int r = 0; r < ndevices; ++r)
+    if (rcs[(size_t)r]) return fail(rcs[(size_t)r], "device " + std::to_string(devices[r]) + ": " + msgs[(size_t)r]);
+  return XCAPE_OK;
+}
 
 extern "C" {
 
@@ -776,32 +809,18 @@ int xcape_cuda_pres_lev_pos(const void* p, const void* ps, int64_t ncol, int nle
                     });
 }
 
-int xcape_cuda_cape(const void* p, const void* t, const void* td, const void* ps, const void* ts, const void* tds,
-                    int64_t ncol, int nlev, int p_is_1d, int dtype, int layout, int mem,
-                    int source, int adiabat, float ml_depth, float pinc, const int32_t* start_3d,
-                    float* cape, float* cin, int32_t* mulev, float* zmulev, int32_t* status, int32_t* n_iter,
-                    int precision, int device, void* stream) {
-  int rc = check_common(ncol, nlev, dtype, layout, mem);
-  if (rc) return rc;
-  if (source < 1 || source > 3) return fail(XCAPE_ERR_ARG, "source must be 1 (surface), 2 (most-unstable) or 3 (mixed-layer)");
-  if (adiabat < 1 || adiabat > 4) return fail(XCAPE_ERR_ARG, "adiabat must be 1..4");
-  if (!(pinc > 0.0f)) return fail(XCAPE_ERR_ARG, "pinc must be > 0");
-  if (precision < XCAPE_FAITHFUL || precision > XCAPE_FAST_OPTIMISTIC) return fail(XCAPE_ERR_ARG, "unknown precision mode");
-  if (ncol == 0) return XCAPE_OK;
-  if (!p || !t || !td || !ps || !ts || !tds || !cape || !cin || !mulev || !zmulev) return fail(XCAPE_ERR_ARG, "null pointer");
-  DeviceGuard dg(device);
-  if (!dg.ok) return fail(XCAPE_ERR_NODEV, "cudaSetDevice failed");
-
-  if (mem == XCAPE_MEM_DEVICE)
-    return cape_device(p, t, td, ps, ts, tds, ncol, nlev, p_is_1d, dtype, layout, ncol, source, adiabat, ml_depth, pinc,
-                       start_3d, cape, cin, mulev, zmulev, status, n_iter, precision, (cudaStream_t)stream);
-
+// Host-pointer CAPE on columns [col0, col0 + ncol) of arrays that hold `pitch` columns (the whole call: col0 = 0, pitch = ncol;
+// a device's shard in xcape_cuda_cape_multi).  The current device is the one the work runs on.
+static int cape_host(const void* p, const void* t, const void* td, const void* ps, const void* ts, const void* tds,
+                     int64_t pitch, int64_t col0, int64_t ncol, int nlev, int p_is_1d, int dtype, int layout,
+                     int source, int adiabat, float ml_depth, float pinc, const int32_t* start_3d,
+                     float* cape, float* cin, int32_t* mulev, float* zmulev, int32_t* status, int32_t* n_iter, int precision) {
   const size_t es = esize(dtype);
   const int lay = base_layout(layout);
   const bool rev = top_first(layout);
   auto host_call = [&](const void* p_, const void* t_, const void* td_, const void* ps_, const void* ts_, const void* tds_,
-                       const int32_t* st3_, int64_t n, int lay_flags, int l0, int nl, float* cape_, float* cin_, int32_t* mulev_,
-                       float* zmulev_, int32_t* status_, int32_t* n_iter_) -> int {
+                       const int32_t* st3_, int64_t n, int64_t pitch_, int64_t col0_, int lay_flags, int l0, int nl, float* cape_,
+                       float* cin_, int32_t* mulev_, float* zmulev_, int32_t* status_, int32_t* n_iter_) -> int {
     std::vector<HostIn3> in3 = {{t_}, {td_}};
     if (!p_is_1d) in3.push_back({p_});
     std::vector<HostIn1> in1 = {{ps_, es}, {ts_, es}, {tds_, es}};
@@ -815,7 +834,7 @@ int xcape_cuda_cape(const void* p, const void* t, const void* td, const void* ps
                                            st3_ ? (const int32_t*)b.in1[3] : nullptr, (float*)b.out[0], (float*)b.out[1],
                                            (int32_t*)b.out[2], (float*)b.out[3], status_ ? (int32_t*)b.out[4] : nullptr,
                                            n_iter_ ? (int32_t*)b.out[5] : nullptr, precision, s, more);
-                      }, l0, nl);
+                      }, l0, nl, pitch_, col0_);
   };
 
   // Ship only the levels the ascent can reach.  The parcel stops at the first level with p <= 100 hPa where it is
@@ -839,22 +858,23 @@ int xcape_cuda_cape(const void* p, const void* t, const void* td, const void* ps
     if (need + 2 <= nlev) { nl = need; l0 = rev ? nlev - need : 0; }
   }
   if (nl == nlev)
-    return host_call(p, t, td, ps, ts, tds, start_3d, ncol, layout, 0, nlev, cape, cin, mulev, zmulev, status, n_iter);
+    return host_call(p, t, td, ps, ts, tds, start_3d, ncol, pitch, col0, layout, 0, nlev, cape, cin, mulev, zmulev, status, n_iter);
 
   static thread_local std::vector<int32_t> own_status;      // reused: a fresh 4 MB vector per call costs 0.3 ms of page faults
+  // status words of this shard, indexed like the caller's arrays (col0 + c)
   int32_t* stat = status;
   if (!stat) {
     if (own_status.size() < (size_t)ncol) own_status.resize((size_t)ncol);
-    stat = own_status.data();
+    stat = own_status.data() - col0;
   }
-  rc = host_call(p, t, td, ps, ts, tds, start_3d, ncol, layout, l0, nl, cape, cin, mulev, zmulev, stat, n_iter);
+  int rc = host_call(p, t, td, ps, ts, tds, start_3d, ncol, pitch, col0, layout, l0, nl, cape, cin, mulev, zmulev, stat, n_iter);
   if (rc) return rc;
   std::vector<int64_t> redo;
   {
     int32_t seen = 0;                              // valid status words are 0..4: OR-ing them finds "any 4" at memory speed
-    for (int64_t c = 0; c < ncol; ++c) seen |= stat[c];
+    for (int64_t c = col0; c < col0 + ncol; ++c) seen |= stat[c];
     if (seen & 4)
-      for (int64_t c = 0; c < ncol; ++c)
+      for (int64_t c = col0; c < col0 + ncol; ++c)
         if (stat[c] == 4) redo.push_back(c);
   }
   if (redo.empty()) return XCAPE_OK;
@@ -868,7 +888,7 @@ int xcape_cuda_cape(const void* p, const void* t, const void* td, const void* ps
     for (int64_t j = 0; j < m; ++j) {
       const int64_t c = redo[(size_t)j];
       if (lay == XCAPE_LEVEL_LAST) memcpy(dst + (size_t)j * nlev * es, (const char*)src + (size_t)c * nlev * es, (size_t)nlev * es);
-      else for (int k = 0; k < nlev; ++k) memcpy(dst + ((size_t)j * nlev + k) * es, (const char*)src + ((size_t)k * ncol + c) * es, es);
+      else for (int k = 0; k < nlev; ++k) memcpy(dst + ((size_t)j * nlev + k) * es, (const char*)src + ((size_t)k * pitch + c) * es, es);
     }
   };
   gather3(t, gt.data()); gather3(td, gtd.data());
@@ -877,7 +897,7 @@ int xcape_cuda_cape(const void* p, const void* t, const void* td, const void* ps
     for (int64_t j = 0; j < m; ++j) memcpy(gs.data() + ((size_t)f * m + j) * es, (const char*)srf[f] + (size_t)redo[(size_t)j] * es, es);
   for (int64_t j = 0; j < m && start_3d; ++j) gst3[(size_t)j] = start_3d[redo[(size_t)j]];
   rc = host_call(p, gt.data(), gtd.data(), gs.data(), gs.data() + (size_t)m * es, gs.data() + (size_t)2 * m * es,
-                 start_3d ? gst3.data() : nullptr, m, XCAPE_LEVEL_LAST | (rev ? XCAPE_LEVELS_TOP_FIRST : 0), 0, nlev,
+                 start_3d ? gst3.data() : nullptr, m, m, 0, XCAPE_LEVEL_LAST | (rev ? XCAPE_LEVELS_TOP_FIRST : 0), 0, nlev,
                  o_cape.data(), o_cin.data(), o_mu.data(), o_z.data(), o_st.data(), o_it.data());
   if (rc) return rc;
   for (int64_t j = 0; j < m; ++j) {
@@ -889,19 +909,59 @@ int xcape_cuda_cape(const void* p, const void* t, const void* td, const void* ps
   return XCAPE_OK;
 }
 
-int xcape_cuda_srh(const void* p, const void* t, const void* td, const void* u, const void* v,
-                   const void* ps, const void* ts, const void* tds, const void* us, const void* vs,
-                   int64_t ncol, int nlev, int p_is_1d, int dtype, int layout, int mem,
-                   double depth, double aglh0, const int32_t* start_3d,
-                   double* srh_rm, double* srh_lm, float* rm, float* lm, float* mean6,
-                   int precision, int device, void* stream) {
+int xcape_cuda_cape(const void* p, const void* t, const void* td, const void* ps, const void* ts, const void* tds,
+                    int64_t ncol, int nlev, int p_is_1d, int dtype, int layout, int mem,
+                    int source, int adiabat, float ml_depth, float pinc, const int32_t* start_3d,
+                    float* cape, float* cin, int32_t* mulev, float* zmulev, int32_t* status, int32_t* n_iter,
+                    int precision, int device, void* stream) {
   int rc = check_common(ncol, nlev, dtype, layout, mem);
   if (rc) return rc;
-  if (precision != XCAPE_FAITHFUL && precision != XCAPE_FAST) return fail(XCAPE_ERR_ARG, "srh: precision must be XCAPE_FAITHFUL or XCAPE_FAST");
+  if (source < 1 || source > 3) return fail(XCAPE_ERR_ARG, "source must be 1 (surface), 2 (most-unstable) or 3 (mixed-layer)");
+  if (adiabat < 1 || adiabat > 4) return fail(XCAPE_ERR_ARG, "adiabat must be 1..4");
+  if (!(pinc > 0.0f)) return fail(XCAPE_ERR_ARG, "pinc must be > 0");
+  if (precision < XCAPE_FAITHFUL || precision > XCAPE_FAST_OPTIMISTIC) return fail(XCAPE_ERR_ARG, "unknown precision mode");
   if (ncol == 0) return XCAPE_OK;
-  if (!p || !t || !td || !u || !v || !ps || !ts || !tds || !us || !vs || !srh_rm || !srh_lm) return fail(XCAPE_ERR_ARG, "null pointer");
+  if (!p || !t || !td || !ps || !ts || !tds || !cape || !cin || !mulev || !zmulev) return fail(XCAPE_ERR_ARG, "null pointer");
   DeviceGuard dg(device);
   if (!dg.ok) return fail(XCAPE_ERR_NODEV, "cudaSetDevice failed");
+
+  if (mem == XCAPE_MEM_DEVICE)
+    return cape_device(p, t, td, ps, ts, tds, ncol, nlev, p_is_1d, dtype, layout, ncol, source, adiabat, ml_depth, pinc,
+                       start_3d, cape, cin, mulev, zmulev, status, n_iter, precision, (cudaStream_t)stream);
+
+  return cape_host(p, t, td, ps, ts, tds, ncol, 0, ncol, nlev, p_is_1d, dtype, layout, source, adiabat, ml_depth, pinc, start_3d,
+                   cape, cin, mulev, zmulev, status, n_iter, precision);
+}
+
+// One host call, several GPUs: contiguous 128-aligned column blocks, one host thread per device, no collective
+// (SURVEY 8e).  Host memory only; both layouts (a level-major shard is addressed through the field's pitch).
+int xcape_cuda_cape_multi(const void* p, const void* t, const void* td, const void* ps, const void* ts, const void* tds,
+                          int64_t ncol, int nlev, int p_is_1d, int dtype, int layout,
+                          int source, int adiabat, float ml_depth, float pinc, const int32_t* start_3d,
+                          float* cape, float* cin, int32_t* mulev, float* zmulev, int32_t* status, int32_t* n_iter,
+                          int precision, const int* devices, int ndevices) {
+  int rc = check_common(ncol, nlev, dtype, layout, XCAPE_MEM_HOST);
+  if (rc) return rc;
+  if (!devices || ndevices < 1) return fail(XCAPE_ERR_ARG, "devices: need at least one device index");
+  if (source < 1 || source > 3) return fail(XCAPE_ERR_ARG, "source must be 1 (surface), 2 (most-unstable) or 3 (mixed-layer)");
+  if (adiabat < 1 || adiabat > 4) return fail(XCAPE_ERR_ARG, "adiabat must be 1..4");
+  if (!(pinc > 0.0f)) return fail(XCAPE_ERR_ARG, "pinc must be > 0");
+  if (precision < XCAPE_FAITHFUL || precision > XCAPE_FAST_OPTIMISTIC) return fail(XCAPE_ERR_ARG, "unknown precision mode");
+  if (ncol == 0) return XCAPE_OK;
+  if (!p || !t || !td || !ps || !ts || !tds || !cape || !cin || !mulev || !zmulev) return fail(XCAPE_ERR_ARG, "null pointer");
+  return run_sharded(ncol, devices, ndevices, [&](int, int64_t c0, int64_t c1) {
+    return cape_host(p, t, td, ps, ts, tds, ncol, c0, c1 - c0, nlev, p_is_1d, dtype, layout, source, adiabat, ml_depth, pinc,
+                     start_3d, cape, cin, mulev, zmulev, status, n_iter, precision);
+  });
+}
+
+// SRH on device pointers (mem == DEVICE: col0 = 0, pitch = ncol) or on columns [col0, col0 + ncol) of host arrays that hold
+// `pitch` columns.  The current device is the one the work runs on.
+static int srh_any(const void* p, const void* t, const void* td, const void* u, const void* v,
+                   const void* ps, const void* ts, const void* tds, const void* us, const void* vs,
+                   int64_t pitch, int64_t col0, int64_t ncol, int nlev, int p_is_1d, int dtype, int layout, int mem,
+                   double depth, double aglh0, const int32_t* start_3d,
+                   double* srh_rm, double* srh_lm, float* rm, float* lm, float* mean6, int precision, cudaStream_t stream) {
   auto dev = [&](const void* p_, const void* t_, const void* td_, const void* u_, const void* v_, const void* ps_,
                  const void* ts_, const void* tds_, const void* us_, const void* vs_, int64_t n, int64_t ld_in,
                  const int32_t* st_, double* srm_, double* slm_, float* rm_, float* lm_, float* m6_, cudaStream_t s) {
@@ -912,7 +972,7 @@ int xcape_cuda_srh(const void* p, const void* t, const void* td, const void* u, 
                                aglh0, st_, srm_, slm_, rm_, lm_, m6_, precision, s);
   };
   if (mem == XCAPE_MEM_DEVICE)
-    return dev(p, t, td, u, v, ps, ts, tds, us, vs, ncol, ncol, start_3d, srh_rm, srh_lm, rm, lm, mean6, (cudaStream_t)stream);
+    return dev(p, t, td, u, v, ps, ts, tds, us, vs, ncol, ncol, start_3d, srh_rm, srh_lm, rm, lm, mean6, stream);
 
   const size_t es = esize(dtype);
   std::vector<HostIn3> in3 = {{t}, {td}, {u}, {v}};
@@ -926,7 +986,48 @@ int xcape_cuda_srh(const void* p, const void* t, const void* td, const void* u, 
                                  b.in1[2], b.in1[3], b.in1[4], n, n, start_3d ? (const int32_t*)b.in1[5] : nullptr,
                                  (double*)b.out[0], (double*)b.out[1], rm ? (float*)b.out[2] : nullptr,
                                  lm ? (float*)b.out[3] : nullptr, mean6 ? (float*)b.out[4] : nullptr, s);
-                    });
+                    }, 0, -1, pitch, col0);
+}
+
+static int srh_check(int64_t ncol, int nlev, int dtype, int layout, int mem, int precision, const void* p, const void* t,
+                     const void* td, const void* u, const void* v, const void* ps, const void* ts, const void* tds,
+                     const void* us, const void* vs, const double* srh_rm, const double* srh_lm) {
+  int rc = check_common(ncol, nlev, dtype, layout, mem);
+  if (rc) return rc;
+  if (precision != XCAPE_FAITHFUL && precision != XCAPE_FAST) return fail(XCAPE_ERR_ARG, "srh: precision must be XCAPE_FAITHFUL or XCAPE_FAST");
+  if (ncol > 0 && (!p || !t || !td || !u || !v || !ps || !ts || !tds || !us || !vs || !srh_rm || !srh_lm)) return fail(XCAPE_ERR_ARG, "null pointer");
+  return XCAPE_OK;
+}
+
+int xcape_cuda_srh(const void* p, const void* t, const void* td, const void* u, const void* v,
+                   const void* ps, const void* ts, const void* tds, const void* us, const void* vs,
+                   int64_t ncol, int nlev, int p_is_1d, int dtype, int layout, int mem,
+                   double depth, double aglh0, const int32_t* start_3d,
+                   double* srh_rm, double* srh_lm, float* rm, float* lm, float* mean6,
+                   int precision, int device, void* stream) {
+  int rc = srh_check(ncol, nlev, dtype, layout, mem, precision, p, t, td, u, v, ps, ts, tds, us, vs, srh_rm, srh_lm);
+  if (rc) return rc;
+  if (ncol == 0) return XCAPE_OK;
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(XCAPE_ERR_NODEV, "cudaSetDevice failed");
+  return srh_any(p, t, td, u, v, ps, ts, tds, us, vs, ncol, 0, ncol, nlev, p_is_1d, dtype, layout, mem, depth, aglh0, start_3d,
+                 srh_rm, srh_lm, rm, lm, mean6, precision, (cudaStream_t)stream);
+}
+
+int xcape_cuda_srh_multi(const void* p, const void* t, const void* td, const void* u, const void* v,
+                         const void* ps, const void* ts, const void* tds, const void* us, const void* vs,
+                         int64_t ncol, int nlev, int p_is_1d, int dtype, int layout,
+                         double depth, double aglh0, const int32_t* start_3d,
+                         double* srh_rm, double* srh_lm, float* rm, float* lm, float* mean6,
+                         int precision, const int* devices, int ndevices) {
+  int rc = srh_check(ncol, nlev, dtype, layout, XCAPE_MEM_HOST, precision, p, t, td, u, v, ps, ts, tds, us, vs, srh_rm, srh_lm);
+  if (rc) return rc;
+  if (!devices || ndevices < 1) return fail(XCAPE_ERR_ARG, "devices: need at least one device index");
+  if (ncol == 0) return XCAPE_OK;
+  return run_sharded(ncol, devices, ndevices, [&](int, int64_t c0, int64_t c1) {
+    return srh_any(p, t, td, u, v, ps, ts, tds, us, vs, ncol, c0, c1 - c0, nlev, p_is_1d, dtype, layout, XCAPE_MEM_HOST, depth, aglh0,
+                   start_3d, srh_rm, srh_lm, rm, lm, mean6, precision, nullptr);
+  });
 }
 
 int xcape_cuda_srh_from_heights(const void* u, const void* v, const void* aglh, const void* us, const void* vs,

@@ -13,7 +13,6 @@ import numpy as np
 
 from . import _array as A
 from . import _lib
-from .sharding import column_blocks, run_on_devices
 
 
 def srh_fused(p_2d, t_2d, td_2d, u_2d, v_2d, p_s, t_s, td_s, u_s, v_s, flag_1d, pres_lev_pos, depth,
@@ -104,7 +103,15 @@ def srh_fused(p_2d, t_2d, td_2d, u_2d, v_2d, p_s, t_s, td_s, u_s, v_s, flag_1d, 
         _lib.check(rc)
 
     if mem == _lib.MEM_HOST and devices is not None and len(devices) > 1:
-        run_on_devices(lambda b, d: call(b[0], b[1], d), column_blocks(ngrid, len(devices)), list(devices))
+        # one C call: contiguous 128-aligned column blocks, one host thread per device (xcape_cuda_srh_multi)
+        opt = lambda a: None if a is None else A.ptr(a)
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        rc = L.xcape_cuda_srh_multi(
+            A.ptr(p), A.ptr(t_), A.ptr(td_), A.ptr(u_), A.ptr(v_), A.ptr(ps_), A.ptr(ts_), A.ptr(tds_), A.ptr(us_), A.ptr(vs_),
+            C.c_int64(ngrid), nlev, p_is_1d, dt, layout | (_lib.LEVELS_TOP_FIRST if top_first else 0),
+            C.c_double(float(depth)), C.c_double(float(aglh0)), opt(start), A.ptr(srm), A.ptr(slm), opt(rm), opt(lm), opt(m6),
+            prec, devs, len(devices))
+        _lib.check(rc)
     else:
         call(0, ngrid, A.device_of(ref, devices[0] if devices else device))
 
