@@ -64,6 +64,35 @@ def test_version_and_error_codes(lib):
         lib.check(cape(source=0))
 
 
+def test_multi_device_entries_validate_without_a_gpu(lib):
+    """xcape_cuda_cape_multi / xcape_cuda_srh_multi: argument errors are reported before any device is touched, an
+    empty grid is a no-op, and a device that does not exist is an error of that device, not a silent skip."""
+    L = lib.lib()
+    z = np.zeros(256, np.float32)
+    zd = np.zeros(256, np.float64)
+    zi = np.zeros(256, np.int32)
+    p = lambda a: a.ctypes.data  # noqa: E731
+    one = (C.c_int * 1)(0)
+
+    def cape(ncol=8, nlev=1, source=1, devices=one, nd=1):
+        return L.xcape_cuda_cape_multi(p(z), p(z), p(z), p(z), p(z), p(z), C.c_int64(ncol), nlev, 0, 0, 0, source, 1,
+                                       C.c_float(500.), C.c_float(500.), None, p(z), p(z), p(zi), p(z), None, None, 0, devices, nd)
+
+    def srh(ncol=8, devices=one, nd=1, precision=0):
+        return L.xcape_cuda_srh_multi(*([p(z)] * 10), C.c_int64(ncol), 1, 0, 0, 0, C.c_double(3000.), C.c_double(2.), None,
+                                      p(zd), p(zd), None, None, None, precision, devices, nd)
+    assert cape(nd=0) == lib.ERR_ARG and b'devices' in L.xcape_cuda_last_error()
+    assert cape(devices=None) == lib.ERR_ARG
+    assert cape(source=7) == lib.ERR_ARG
+    assert cape(ncol=0) == lib.OK
+    assert srh(nd=0) == lib.ERR_ARG
+    assert srh(precision=2) == lib.ERR_ARG
+    assert srh(ncol=0) == lib.OK
+    if lib.device_count() < 1:
+        rc = cape(ncol=8)                                  # no GPU here: the shard's device cannot be selected
+        assert rc != lib.OK and b'device 0' in L.xcape_cuda_last_error()
+
+
 def test_missing_extension_fails_loudly(lib, monkeypatch):
     monkeypatch.setattr(lib, '_lib', None)
     monkeypatch.setattr(lib, 'LIB_PATH', '/nonexistent/libxcape_b200.so')
