@@ -376,6 +376,39 @@ __device__ __forceinline__ void col2_store(const CapeArgs& a, const Col2& C) {
   if (a.n_iter) a.n_iter[C.c] = C.iters;
 }
 
+// The window loop of one sub-step for both halves (f90:436-474 inside the window): returns the last pass's values, per
+// half the `left` counter at the last pass that ended with the half still moving, and whether a window was left.
+struct WinOut { f2 t2, th2, qv2, ql2, qi2; int lx, ly; bool left_window; };
+template <bool ICE, bool PSEUDO>
+__device__ __forceinline__ WinOut window_loop(f2 pi2, f2 p2, f2 qt, f2 t1, f2 th1, f2 qv1, f2 ql1, f2 qi1, f2 logp, float tmx, f2 one) {
+  WinOut o;
+  f2 thlast = th1;
+  // the window's accumulators are shared by the two halves (leaving it is rare, and the general loop is always right):
+  // 90 <= every t2 <= the smaller tmax, every |arg| <= 2^-6
+  float t_hi = 90.0f, t_lo = 400.0f, a_hi = 0.0f;
+  int lx = 101, ly = 101;                     // `left` at the last pass that ended with the half still moving
+  int left = 100;
+  bool mx, my;
+  do {
+    o.t2 = vmul(thlast, pi2);
+    t_hi = fmaxf(t_hi, fmaxf(o.t2.x, o.t2.y)); t_lo = fminf(t_lo, fminf(o.t2.x, o.t2.y));      // FMNMX3
+    const f2 arg = vmoist_arg<ICE, PSEUDO>(o.t2, p2, qt, t1, qv1, ql1, qi1, logp, o.qv2, o.ql2, o.qi2, one);
+    a_hi = fmaxf(a_hi, fmaxf(fabsf(arg.x), fabsf(arg.y)));
+    o.th2 = vmul(th1, vexp32_tiny(arg));
+    const f2 d = vsubx(o.th2, thlast, one);
+    const f2 step = vmul(d, 0.3f);
+    mx = fabsf(d.x) > cc::converge; my = fabsf(d.y) > cc::converge;
+    // a half that has converged keeps its thlast: the following passes recompute its final pass unchanged
+    if (mx) { thlast.x = thlast.x + step.x; lx = left; }
+    if (my) { thlast.y = thlast.y + step.y; ly = left; }
+    left = left - 1;
+  } while ((mx || my) && left != 0);
+  // pass k runs with left = 101 - k: the half took (101 - l) + 1 passes, or was still moving at pass 100 (l == 1)
+  o.lx = lx; o.ly = ly;
+  o.left_window = !(t_lo >= 90.0f) || !(t_hi <= tmx) || !(a_hi <= 0.015625f);
+  return o;
+}
+
 #ifndef XC_CAPE2_THREADS
 #define XC_CAPE2_THREADS 128
 #endif
@@ -425,59 +458,40 @@ __global__ void __launch_bounds__(XC_CAPE2_THREADS, XC_CAPE2_MIN_BLOCKS) cape_ke
       bool genA = doA, genB = doB;
       int iA = 0, iB = 0;
 
-      if (SA.window || SB.window) {
-        // ---- window loop, both columns in packed arithmetic.  A column that does not take part rides along
-        // as a copy of the other one (identical arithmetic, so it neither delays convergence nor matters).
-        const bool wa = SA.window, wb = SB.window;
-        const f2 pi2 = make_float2(wa ? A.pi2 : B.pi2, wb ? B.pi2 : A.pi2);
-        const f2 p2 = make_float2(wa ? A.p2 : B.p2, wb ? B.p2 : A.p2);
-        const f2 qt = make_float2(wa ? A.qt : B.qt, wb ? B.qt : A.qt);
-        const f2 t1 = make_float2(wa ? SA.t1 : SB.t1, wb ? SB.t1 : SA.t1);
-        const f2 th1 = make_float2(wa ? SA.th1 : SB.th1, wb ? SB.th1 : SA.th1);
-        const f2 qv1 = make_float2(wa ? SA.qv1 : SB.qv1, wb ? SB.qv1 : SA.qv1);
-        const f2 ql1 = make_float2(wa ? SA.ql1 : SB.ql1, wb ? SB.ql1 : SA.ql1);
-        const f2 qi1 = make_float2(wa ? SA.qi1 : SB.qi1, wb ? SB.qi1 : SA.qi1);
-        const f2 logp = make_float2(wa ? SA.logp : SB.logp, wb ? SB.logp : SA.logp);
-        // the window's accumulators are shared by the two halves (leaving it is rare, and the general loop is always right):
-        // 90 <= every t2 <= the smaller tmax, every |arg| <= 2^-6
-        const float tmx = fminf(wa ? YA.tmax : YB.tmax, wb ? YB.tmax : YA.tmax);
-        const f2 one = a.one2;
-        f2 thlast = th1;
-        float t_hi = 90.0f, t_lo = 400.0f, a_hi = 0.0f;
-        f2 t2, th2, qv2, ql2, qi2;
-        int lx = 101, ly = 101;                     // `left` at the last pass that ended with the half still moving
-        int left = 100;
-        bool mx, my;
-        do {
-          t2 = vmul(thlast, pi2);
-          t_hi = fmaxf(t_hi, fmaxf(t2.x, t2.y)); t_lo = fminf(t_lo, fminf(t2.x, t2.y));      // FMNMX3
-          const f2 arg = vmoist_arg<ICE, PSEUDO>(t2, p2, qt, t1, qv1, ql1, qi1, logp, qv2, ql2, qi2, one);
-          a_hi = fmaxf(a_hi, fmaxf(fabsf(arg.x), fabsf(arg.y)));
-          th2 = vmul(th1, vexp32_tiny(arg));
-          const f2 d = vsubx(th2, thlast, one);
-          const f2 step = vmul(d, 0.3f);
-          mx = fabsf(d.x) > cc::converge; my = fabsf(d.y) > cc::converge;
-          // a half that has converged keeps its thlast: the following passes recompute its final pass unchanged
-          if (mx) { thlast.x = thlast.x + step.x; lx = left; }
-          if (my) { thlast.y = thlast.y + step.y; ly = left; }
-          left = left - 1;
-        } while ((mx || my) && left != 0);
-        // pass k runs with left = 101 - k: the half took (101 - l) + 1 passes, or was still moving at pass 100 (l == 1)
-        const bool left_window = !(t_lo >= 90.0f) || !(t_hi <= tmx) || !(a_hi <= 0.015625f);
-        if (wa) {
-          genA = left_window;
-          if (!genA) {
-            A.t2 = t2.x; A.th2 = th2.x; A.qv2 = qv2.x; A.ql2 = ql2.x; A.qi2 = qi2.x;
-            iA = 102 - lx;
-            if (lx == 1) { iA = 101; A.st = 2; }    // the reference runs pass 101 and gives up there (f90:464-474)
-          }
+      if (SA.window && SB.window) {
+        // ---- the usual case after sorting: both columns inside their windows.  Operands packed without selects; when no
+        // window was left and neither half ran into the cap, the sub-step's epilogue is straight-line code.
+        const WinOut w = window_loop<ICE, PSEUDO>(make_float2(A.pi2, B.pi2), make_float2(A.p2, B.p2), make_float2(A.qt, B.qt),
+                                                  make_float2(SA.t1, SB.t1), make_float2(SA.th1, SB.th1), make_float2(SA.qv1, SB.qv1),
+                                                  make_float2(SA.ql1, SB.ql1), make_float2(SA.qi1, SB.qi1),
+                                                  make_float2(SA.logp, SB.logp), fminf(YA.tmax, YB.tmax), a.one2);
+        if (!w.left_window && w.lx != 1 && w.ly != 1) {
+          A.t2 = w.t2.x; A.th2 = w.th2.x; A.qv2 = w.qv2.x; A.ql2 = w.ql2.x; A.qi2 = w.qi2.x;
+          B.t2 = w.t2.y; B.th2 = w.th2.y; B.qv2 = w.qv2.y; B.ql2 = w.ql2.y; B.qi2 = w.qi2.y;
+          col2_sub_end<PSEUDO>(A, 102 - w.lx);
+          col2_sub_end<PSEUDO>(B, 102 - w.ly);
+          continue;
         }
-        if (wb) {
-          genB = left_window;
-          if (!genB) {
-            B.t2 = t2.y; B.th2 = th2.y; B.qv2 = qv2.y; B.ql2 = ql2.y; B.qi2 = qi2.y;
-            iB = 102 - ly;
-            if (ly == 1) { iB = 101; B.st = 2; }
+        // a window was left or a half is still moving after 100 passes: both columns take the reference's loop verbatim
+      } else if (SA.window || SB.window) {
+        // ---- one column inside its window: it is lifted in packed arithmetic with a copy of itself in the other half
+        // (identical arithmetic, so the copy neither delays convergence nor matters)
+        const bool wa = SA.window;
+        const Col2& C = wa ? A : B;
+        const Sub2& S = wa ? SA : SB;
+        const WinOut w = window_loop<ICE, PSEUDO>(splat(C.pi2), splat(C.p2), splat(C.qt), splat(S.t1), splat(S.th1), splat(S.qv1),
+                                                  splat(S.ql1), splat(S.qi1), splat(S.logp), wa ? YA.tmax : YB.tmax, a.one2);
+        if (!w.left_window) {
+          if (wa) {
+            genA = false;
+            A.t2 = w.t2.x; A.th2 = w.th2.x; A.qv2 = w.qv2.x; A.ql2 = w.ql2.x; A.qi2 = w.qi2.x;
+            iA = 102 - w.lx;
+            if (w.lx == 1) { iA = 101; A.st = 2; }    // the reference runs pass 101 and gives up there (f90:464-474)
+          } else {
+            genB = false;
+            B.t2 = w.t2.x; B.th2 = w.th2.x; B.qv2 = w.qv2.x; B.ql2 = w.ql2.x; B.qi2 = w.qi2.x;
+            iB = 102 - w.lx;
+            if (w.lx == 1) { iB = 101; B.st = 2; }
           }
         }
       }
