@@ -2,6 +2,7 @@
 // canonicalisation of dtype/layout on the device, kernel dispatch, and the host-pointer
 // path (column blocks staged H2D / computed / D2H on a ring of streams).
 #include <algorithm>
+#include <cstdint>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -735,12 +736,17 @@ static int run_sharded(int64_t ncol, const int* devices, int ndevices, F fn) {
     int64_t c0, c1;
     shard_block(ncol, ndevices, r, &c0, &c1);
     if (c1 <= c0) continue;
-    th.emplace_back([&, r, c0, c1] {
+    auto work = [&, r, c0, c1] {
       DeviceGuard dg(devices[r]);
       if (!dg.ok) { rcs[(size_t)r] = XCAPE_ERR_NODEV; msgs[(size_t)r] = "cudaSetDevice failed"; return; }
       rcs[(size_t)r] = fn(r, c0, c1);
       if (rcs[(size_t)r]) msgs[(size_t)r] = g_last_error;      // thread-local: carry it to the caller's thread
-    });
+    };
+    try {
+      th.emplace_back(work);
+    } catch (...) {                                          // no thread to be had: run the block here (no exception may cross the C ABI)
+      work();
+    }
   }
   for (auto& x : th) x.join();
   for (int r = 0; r < ndevices; ++r)
@@ -865,7 +871,8 @@ static int cape_host(const void* p, const void* t, const void* td, const void* p
   int32_t* stat = status;
   if (!stat) {
     if (own_status.size() < (size_t)ncol) own_status.resize((size_t)ncol);
-    stat = own_status.data() - col0;
+    // run_staged addresses every host array at (col0 + c): bias the shard-local buffer so that element col0 is its first
+    stat = (int32_t*)((uintptr_t)own_status.data() - (uintptr_t)col0 * sizeof(int32_t));
   }
   int rc = host_call(p, t, td, ps, ts, tds, start_3d, ncol, pitch, col0, layout, l0, nl, cape, cin, mulev, zmulev, stat, n_iter);
   if (rc) return rc;
