@@ -10,19 +10,24 @@
 // order was.  Columns that do not ascend at all (ts <= 0 degC gate, parcel on the top level) go to the end of their
 // window, so whole warps of them leave at once instead of idling beside working lanes.
 //
-// The order is established inside WINDOWS of 16384 consecutive columns, not globally: the ascent kernel's per-level
-// loads become gathers (a 32-byte sector for 4 bytes), and the other seven columns of a sector are then lifted by
-// CTAs of the same window at about the same time, so the sector is served by L2 instead of crossing HBM eight times
-// (a global order was measured: ERA5 pressure levels fine, HRRR 50 sigma levels 15.8 -> 17.4 ms).  A window is also
-// what one CTA can sort in shared memory.
+// Two ways to establish the order (the launcher in cape_faithful.cu picks; XCAPE_B200_SORT_MODE overrides):
+//  * GLOBAL, pressure grids (a shared pressure axis of <= 64 levels): counting sort over the whole call by (start level,
+//    theta-e in 0.1 K bins) — histogram by atomics in the source kernel, a two-kernel exclusive scan, an atomic scatter.
+//    Positions inside a bin follow the atomics' order: grouping (and timing) may differ from run to run, results cannot.
+//  * WINDOWS of 16384 consecutive columns, sigma grids: one CTA per window sorts (key << 32 | index) in shared memory
+//    (bitonic network; deterministic).  Windows exist because the ascent kernel's per-level loads become gathers (a
+//    32-byte sector for 4 bytes): the other seven columns of a sector must be lifted by CTAs running at the same time for
+//    the sector to come from L2 instead of crossing HBM eight times.  Measured: a global order costs HRRR (50 sigma
+//    levels x 3 fields) 15.8 -> 17.2 ms where windows give 14.8; ERA5 (<= 27 levels x 2 fields reached) gains 0.28 ms from the
+//    global order over windows (profiles/r2m_lab_sort_modes.txt).
 //
 // Pipeline (all on the caller's stream, scratch from the caller):
 //   1. cape_source_kernel   storage order, coalesced: gate, start level, source parcel (the scalar code of
-//                           cape_kernel.cuh, run once per column) -> parcel record + 32-bit key
-//   2. cape_window_sort_kernel  one CTA per window: bitonic sort of (key << 32 | column) in shared memory -> perm[]
+//                           cape_kernel.cuh, run once per column) -> parcel record + 32-bit key (+ histogram)
+//   2. the order            cape_scan_totals_kernel + cape_scan_kernel + cape_scatter_kernel, or cape_window_sort_kernel -> perm[]
 //   3. cape_kernel2<SORTED> thread t lifts columns perm[2t], perm[2t+1] from their records
 // The key only decides which columns share a warp; results are per-column and bit-identical to the unsorted run
-// (tests/test_gpu_parity.py::test_sorted_execution_matches_storage_order).  The sort is deterministic.
+// (tests/test_gpu_parity.py::test_sorted_execution_matches_storage_order, both orders).
 #pragma once
 #include "cape_kernel2.cuh"
 
