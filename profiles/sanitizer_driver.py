@@ -50,5 +50,26 @@ for cfg, vlev in (('C2', 'pressure'), ('C3', 'sigma')):
     dewpoint_from_q(d['p'] if vlev == 'pressure' else np.ascontiguousarray(d['p'].T), np.ascontiguousarray(q.T), lev_axis=0)
     dewpoint_from_q(torch.from_numpy(d['p']).cuda() if vlev == 'pressure' else torch.from_numpy(d['p']).cuda(),
                     torch.from_numpy(q).cuda())
+# round 2: sorted execution of the faithful kernel (both orders, forced for this small size), the SRH tile kernel against
+# the relayout path, the multi-device entries (one device listed twice)
+for cfg, vlev in (('C2', 'pressure'), ('C3', 'sigma')):
+    d = make_soundings(cfg, cols=(0, 1500 + 37), active=False)
+    args = (d['p'], d['t'], d['td'], d['ps'], d['ts'], d['tds'])
+    for mode in ('global', 'window'):
+        os.environ.update(XCAPE_B200_SORT='1', XCAPE_B200_SORT_MODE=mode)
+        for src in ('surface', 'most-unstable', 'mixed-layer'):
+            core.calc_cape(*args, source=src, vertical_lev=vlev, method='cuda')
+        core.calc_cape(*args, source='most-unstable', adiabat='reversible-ice', vertical_lev=vlev, method='cuda')
+        core.calc_cape(*[torch.from_numpy(a).cuda() for a in args], source='most-unstable', vertical_lev=vlev, method='cuda')
+        core.calc_cape(*args, source='most-unstable', vertical_lev=vlev, method='cuda', devices=[0, 0])
+    for k in ('XCAPE_B200_SORT', 'XCAPE_B200_SORT_MODE'):
+        os.environ.pop(k, None)
+    sargs = tuple(d[k] for k in ('p', 't', 'td', 'u', 'v', 'ps', 'ts', 'tds', 'us', 'vs'))
+    for tile in ('1', '0'):
+        os.environ['XCAPE_B200_SRH_TILE'] = tile
+        core.calc_srh(*sargs, vertical_lev=vlev, output_var='all', method='cuda')
+        core.calc_srh(*(a.astype(np.float64) for a in sargs), vertical_lev=vlev, output_var='all', method='cuda')
+    os.environ.pop('XCAPE_B200_SRH_TILE', None)
+    core.calc_srh(*sargs, vertical_lev=vlev, output_var='all', method='cuda', devices=[0, 0])
 torch.cuda.synchronize()
 print('sanitizer driver done')
