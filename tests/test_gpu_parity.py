@@ -652,6 +652,33 @@ def test_fast_mode_goldens(core, soundings, era5pl):
         core.calc_cape(*era_cape_args(era5pl), vertical_lev='pressure', method='cuda', precision='sloppy')
 
 
+# ------------------------------------------------------------------ kernel-alone timing through the C ABI
+def test_kernel_timer_reports_the_dominant_kernel(core):
+    """xcape_cuda_time_kernels / xcape_cuda_last_kernel_ms (what bench.py's roofline leg uses): after a timed device-pointer
+    call the ascent kernel's device time is positive and below the call's own event-timed duration; without timing the
+    query fails instead of returning a stale number."""
+    import torch
+    from xcape_b200 import _lib
+    from xcape_b200.cape_cuda import cape as cape_cuda, pres_lev_pos
+    from xcape_b200.synthetic import make_soundings
+    d = make_soundings('C2', cols=(0, 100_000))
+    dev = torch.device('cuda', 0)
+    t, td = (torch.from_numpy(d[k]).to(dev).t().contiguous() for k in ('t', 'td'))
+    p, ps, ts, tds = (torch.from_numpy(d[k]).to(dev) for k in ('p', 'ps', 'ts', 'tds'))
+    plp = pres_lev_pos(p, ps)
+    run = lambda: cape_cuda(p, t, td, ps, ts, tds, 1, plp, 2, 500., 1, 500., 2)
+    run(); torch.cuda.synchronize()
+    _lib.time_kernels(True)
+    try:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(); e1.record()
+        ms_kernel = _lib.last_kernel_ms()
+        torch.cuda.synchronize()
+        assert 0.0 < ms_kernel <= e0.elapsed_time(e1)
+    finally:
+        _lib.time_kernels(False)
+
+
 # ------------------------------------------------------------------ several GPUs in one process
 def test_devices_kwarg_shards_columns_over_gpus(core):
     """`devices=[0, 1, ...]`: contiguous 128-aligned column blocks, one host thread per GPU, no
