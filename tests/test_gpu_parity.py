@@ -655,8 +655,7 @@ def test_fast_mode_goldens(core, soundings, era5pl):
 # ------------------------------------------------------------------ kernel-alone timing through the C ABI
 def test_kernel_timer_reports_the_dominant_kernel(core):
     """xcape_cuda_time_kernels / xcape_cuda_last_kernel_ms (what bench.py's roofline leg uses): after a timed device-pointer
-    call the ascent kernel's device time is positive and below the call's own event-timed duration; without timing the
-    query fails instead of returning a stale number."""
+    call the ascent kernel's device time is positive and below the call's own event-timed duration."""
     import torch
     from xcape_b200 import _lib
     from xcape_b200.cape_cuda import cape as cape_cuda, pres_lev_pos
