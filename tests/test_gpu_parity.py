@@ -502,7 +502,8 @@ def test_srh_two_call_form_matches_fused_and_oracle(core, oracle_mod, cfg, type_
 @pytest.mark.parametrize('cfg,vertical_lev', [('C3', 'sigma'), ('C2', 'pressure'), ('C5', 'sigma')])
 @pytest.mark.parametrize('dtype', [np.float32, np.float64])
 @pytest.mark.parametrize('precision', ['faithful', 'fast'])
-def test_srh_tile_kernel_matches_relayout_path(core, cfg, vertical_lev, dtype, precision, monkeypatch):
+@pytest.mark.parametrize('level_order', ['surface_first', 'top_first'])
+def test_srh_tile_kernel_matches_relayout_path(core, cfg, vertical_lev, dtype, precision, level_order, monkeypatch):
     """Reference-layout (level-last) input is read in place by the tile kernel (srh_tile.cuh); XCAPE_B200_SRH_TILE=0
     re-lays the fields out and runs the level-major kernel.  Same per-column arithmetic, so every output is the
     same bit for bit — odd column counts (a partial tile), odd and even level counts, start levels above the
@@ -514,10 +515,16 @@ def test_srh_tile_kernel_matches_relayout_path(core, cfg, vertical_lev, dtype, p
         p[::5, 7] = p[::5, 6]                         # duplicate level
         p[1::11, 12] = p[1::11, 10] + 1.0             # out of order
     args = tuple(a.astype(dtype) for a in (p, d['t'], d['td'], d['u'], d['v'], d['ps'], d['ts'], d['tds'], d['us'], d['vs']))
+    ref_order = core.calc_srh(*args, depth=3000, vertical_lev=vertical_lev, output_var='all', method='cuda', precision=precision)
+    if level_order == 'top_first':                     # the level axis stored model top first (ERA5 downloads): walked backwards in place
+        args = tuple(np.ascontiguousarray(a[..., ::-1]) for a in args[:5]) + args[5:]
     out = {}
     for tile in ('1', '0'):
         monkeypatch.setenv('XCAPE_B200_SRH_TILE', tile)
-        out[tile] = core.calc_srh(*args, depth=3000, vertical_lev=vertical_lev, output_var='all', method='cuda', precision=precision)
+        out[tile] = core.calc_srh(*args, depth=3000, vertical_lev=vertical_lev, output_var='all', method='cuda', precision=precision,
+                                  level_order=level_order)
+    for i, (a, b) in enumerate(zip(out['1'], ref_order)):
+        assert np.array_equal(a, b, equal_nan=True), f'output {i} depends on the storage order of the level axis' 
     assert len(out['1']) == len(out['0']) == 8
     for i, (a, b) in enumerate(zip(out['1'], out['0'])):
         assert np.array_equal(a, b, equal_nan=True), f'output {i}: {(a != b).sum()} elements differ, max {np.nanmax(np.abs(a - b))}'

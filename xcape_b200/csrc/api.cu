@@ -253,13 +253,17 @@ int srh_device_t(const void* p, const void* t, const void* td, const void* u, co
   int rc;
   const void* q;
   int64_t ld = ncol, l2 = ncol;
-  // reference layout (level-last), surface first: read in place by the tile kernel (srh_tile.cuh) — no relayout.
+  // reference layout (level-last), either level order: read in place by the tile kernel (srh_tile.cuh) — no relayout.
   // XCAPE_B200_SRH_TILE=0 selects relayout + level-major kernel (A/B, tests).
   const char* tile_env = getenv("XCAPE_B200_SRH_TILE");
-  const bool tile = base_layout(layout) == XCAPE_LEVEL_LAST && !top_first(layout) && !(tile_env && tile_env[0] == '0');
+  const bool tile = base_layout(layout) == XCAPE_LEVEL_LAST && !(tile_env && tile_env[0] == '0');
   if (tile) {
-    a.t = (const T*)t; a.td = (const T*)td; a.u = (const T*)u; a.v = (const T*)v; a.p = (const T*)p;
-    a.lev_stride = 1; a.col_stride = nlev;
+    // stored top first: point at each column's last stored level and walk the level axis backwards (stride -1)
+    const int64_t o = top_first(layout) ? nlev - 1 : 0;
+    a.t = (const T*)t + o; a.td = (const T*)td + o; a.u = (const T*)u + o; a.v = (const T*)v + o;
+    if (p_is_1d) { if ((rc = canon_p1d(p, dtype, layout, nlev, sc, &q, s))) return rc; p = q; a.p = (const T*)q; }   // flipped copy of nlev elements
+    else a.p = (const T*)p + o;
+    a.lev_stride = top_first(layout) ? -1 : 1; a.col_stride = nlev;
   } else {
     if ((rc = canon3d_same(t, dtype, layout, ncol, nlev, ld_in, sc, &q, &ld, s))) return rc; a.t = (const T*)q;
     if ((rc = canon3d_same(td, dtype, layout, ncol, nlev, ld_in, sc, &q, &l2, s))) return rc; a.td = (const T*)q;

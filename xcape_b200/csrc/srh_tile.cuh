@@ -11,7 +11,7 @@
 // while this one is computed; 42 KB), not the column, so five CTAs stay resident per SM and the FP64 chain keeps its
 // latency hiding; every input byte crosses HBM once, and
 // levels above the last one any column of the tile needs (6 km / depth) are not read at all (only their pressures,
-// for the monotonicity check).
+// for the monotonicity check).  A level axis stored top first (ERA5 downloads) is walked backwards in place.
 #pragma once
 #include "srh_kernel.cuh"
 
@@ -39,15 +39,17 @@ template <class T> __device__ __forceinline__ void cp_async_elem(T* smem_dst, co
   if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
   else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
 }
+// `ls` = +1: levels stored surface first; -1: stored top first, `g` then points at the LAST stored level of column 0
+// (the level axis is walked backwards, as everywhere else in the library; pieces stay contiguous, only reversed)
 template <class T, int KC>
-__device__ __forceinline__ void tile_load_async(const T* __restrict__ g, int64_t c0, int ncols, int nlev, int k0,
+__device__ __forceinline__ void tile_load_async(const T* __restrict__ g, int64_t c0, int ncols, int nlev, int k0, int ls,
                                                 T (*s)[kTileCols + kTilePad]) {
   const T* base = g + c0 * nlev;
 #pragma unroll
   for (int e = threadIdx.x; e < kTileCols * KC; e += kTileCols) {
     const int col = e / KC, kk = e % KC;
     const int k = k0 + kk;
-    if (col < ncols && k < nlev) cp_async_elem(&s[kk][col], base + (int64_t)col * nlev + k);
+    if (col < ncols && k < nlev) cp_async_elem(&s[kk][col], base + (int64_t)col * nlev + k * ls);
   }
 }
 
@@ -71,12 +73,13 @@ __global__ void __launch_bounds__(kTileCols, XC_SRH_TILE_MIN_BLOCKS) srh_tile_ke
   bool all_done = false;           // no column of the tile needs t / td / u / v any more
   auto issue = [&](int k0, int buf) {
     if (k0 < a.nlev) {
-      if (!P1D) tile_load_async<T, KC>(a.p, c0, ncols, a.nlev, k0, sP[buf]);
+      const int ls = (int)a.lev_stride;                 // +1 / -1
+      if (!P1D) tile_load_async<T, KC>(a.p, c0, ncols, a.nlev, k0, ls, sP[buf]);
       if (!all_done) {
-        tile_load_async<T, KC>(a.t, c0, ncols, a.nlev, k0, sT[buf]);
-        tile_load_async<T, KC>(a.td, c0, ncols, a.nlev, k0, sTd[buf]);
-        tile_load_async<T, KC>(a.u, c0, ncols, a.nlev, k0, sU[buf]);
-        tile_load_async<T, KC>(a.v, c0, ncols, a.nlev, k0, sV[buf]);
+        tile_load_async<T, KC>(a.t, c0, ncols, a.nlev, k0, ls, sT[buf]);
+        tile_load_async<T, KC>(a.td, c0, ncols, a.nlev, k0, ls, sTd[buf]);
+        tile_load_async<T, KC>(a.u, c0, ncols, a.nlev, k0, ls, sU[buf]);
+        tile_load_async<T, KC>(a.v, c0, ncols, a.nlev, k0, ls, sV[buf]);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
