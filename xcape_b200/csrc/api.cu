@@ -177,17 +177,34 @@ int cape_device(const void* p, const void* t, const void* td, const void* ps, co
   int rc;
   int64_t ld = ncol, ldp = ncol;
   const float* q;
-  if ((rc = canon3d(t, dtype, layout, ncol, nlev, ld_in, sc, &q, &ld, s))) return rc; a.t = q;
-  int64_t ld2 = ncol;
-  if ((rc = canon3d(td, dtype, layout, ncol, nlev, ld_in, sc, &q, &ld2, s))) return rc; a.td = q;
+  a.cs = 1;
+  // The reference's level-last float32 layout is read IN PLACE by the sorted execution of the faithful kernel: there every
+  // thread walks its own column, whose levels are contiguous, so the loads that are gathers on a level-major copy become
+  // sector-sequential reads served by L1 — and the two or three relayout launches (2 x the field through HBM) disappear.
+  // (Storage-order execution keeps the level-major copy: adjacent threads = adjacent columns = coalesced loads.)
+  const char* direct_env = getenv("XCAPE_B200_CAPE_DIRECT");
+  const bool direct = dtype == XCAPE_F32 && base_layout(layout) == XCAPE_LEVEL_LAST && precision == XCAPE_FAITHFUL &&
+                      cape_sort_scratch_bytes(ncol, nlev) > 0 && !(direct_env && direct_env[0] == '0');
+  if (direct) {
+    const int64_t o = top_first(layout) ? nlev - 1 : 0;     // stored top first: start at each column's last stored level, stride -1
+    a.t = (const float*)t + o; a.td = (const float*)td + o;
+    ld = top_first(layout) ? -1 : 1; a.cs = nlev;
+  } else {
+    if ((rc = canon3d(t, dtype, layout, ncol, nlev, ld_in, sc, &q, &ld, s))) return rc; a.t = q;
+    int64_t ld2 = ncol;
+    if ((rc = canon3d(td, dtype, layout, ncol, nlev, ld_in, sc, &q, &ld2, s))) return rc; a.td = q;
+    if (ld2 != ld) return fail(XCAPE_ERR_ARG, "internal: inconsistent leading dimensions");
+  }
   if (p_is_1d) {
     const void* pv;
     if ((rc = canon_p1d(p, dtype, layout, nlev, sc, &pv, s))) return rc; p = pv;
     if ((rc = canon1d(p, dtype, nlev, sc, &q, s))) return rc; a.p = q;
+  } else if (direct) {
+    a.p = (const float*)p + (top_first(layout) ? nlev - 1 : 0);
   } else {
     if ((rc = canon3d(p, dtype, layout, ncol, nlev, ld_in, sc, &q, &ldp, s))) return rc; a.p = q;
+    if (ldp != ld) return fail(XCAPE_ERR_ARG, "internal: inconsistent leading dimensions");
   }
-  if (ld2 != ld || (!p_is_1d && ldp != ld)) return fail(XCAPE_ERR_ARG, "internal: inconsistent leading dimensions");
   if ((rc = canon1d(ps, dtype, ncol, sc, &q, s))) return rc; a.ps = q;
   if ((rc = canon1d(ts, dtype, ncol, sc, &q, s))) return rc; a.ts = q;
   if ((rc = canon1d(tds, dtype, ncol, sc, &q, s))) return rc; a.tds = q;

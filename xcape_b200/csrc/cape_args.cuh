@@ -25,7 +25,9 @@ struct CapeArgs {
   const float* __restrict__ tds;
   const int32_t* __restrict__ start;   // [ncol] 1-based first level used, or nullptr (=1)
   int64_t ncol;
-  int64_t ld;                      // distance (elements) between consecutive levels
+  int64_t ld;                      // distance (elements) between consecutive levels (negative: the level axis is stored top first)
+  int64_t cs;                      // distance (elements) between consecutive columns: 1 = level-major; nlev = the reference's
+                                   // level-last layout read in place (element (lev, c) at lev * ld + c * cs, ld = +-1)
   int nlev;
   float pinc;
   float ml_depth;
