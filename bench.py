@@ -17,7 +17,7 @@ shards time chunks / column blocks, no collective).
 Numbers on the JSON line:
   value      whole-job columns/s with the field resident in HBM in the reference's own layout
              ([ncol, nlev] float32, level last); the timed call is the public device-pointer
-             path (pres_lev_pos + relayout + kernel), CUDA events on the launch stream.
+             path (pres_lev_pos + the sorted call reading the layout in place: source-parcel kernel, ordering, ascent kernel), CUDA events on the launch stream.
   e2e        same metric through the PUBLIC call a user makes, core.calc_cape / core.calc_srh(method='cuda'),
              on pinned host numpy arrays in the reference's layout ([ncol, nlev], level last): host numpy in,
              host numpy out, H2D / D2H inside the timed region.  Sub-records: `pageable` (ordinary numpy
