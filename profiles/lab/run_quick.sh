@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 {
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "sorted_execution or full_field_bitexact or two_column or every_source or c1_ or garbage or edge or pinc" 2>&1 | tail -2
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "sorted_execution or full_field_bitexact or two_column or every_source or c1_ or garbage or edge or pinc or fast_mode or golden" 2>&1 | tail -2
 python profiles/lab_time_kernel.py C2 2 10
 LAB_SHUFFLE=1 python profiles/lab_time_kernel.py C2 2 10
 python profiles/lab_time_kernel.py C3 3 5
