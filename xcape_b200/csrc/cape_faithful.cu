@@ -83,7 +83,7 @@ static int launch(const CapeArgs& a, cudaStream_t s) {
         XC_LAUNCH_CHECK();
         cape_scan_kernel<<<ntiles, 1024, 0, s>>>(b.hist, b.tile_total);
         XC_LAUNCH_CHECK();
-        cape_scatter_kernel<<<(unsigned)((a.ncol + 255) / 256), 256, 0, s>>>(b.key, b.hist, b.perm, a.ncol);
+        cape_scatter_kernel<<<(unsigned)((a.ncol + 255) / 256), 256, 0, s>>>(b.key, b.hist, b.perm, a.ncol, (uint32_t)(b.nbins - 1));
         XC_LAUNCH_CHECK();
       } else {
         static std::once_flag smem_once[64];
